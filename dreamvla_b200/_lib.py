@@ -1,0 +1,305 @@
+"""ctypes binding of libdvla_sm100.so (include/dvla.h).  This is the only place Python touches the C ABI.
+
+The product path has NO fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+PyTorch is used for device memory and streams only (tensor.data_ptr(), torch.cuda.current_stream()).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdvla_sm100.so")
+
+ACT_NONE, ACT_GELU_ERF, ACT_GELU_TANH, ACT_QUICK_GELU, ACT_RELU, ACT_SILU = range(6)
+ACT_IDS = {None: 0, "none": 0, "gelu": 1, "gelu_erf": 1, "gelu_tanh": 2, "gelu_new": 2, "quick_gelu": 3, "relu": 4,
+           "silu": 5}
+
+_vp, _i64, _i32, _f32, _u64 = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_uint64
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("a", _vp), ("b", _vp), ("out", _vp), ("bias", _vp), ("residual", _vp), ("aux_out", _vp),
+                ("aux_in", _vp), ("M", _i64), ("N", _i64), ("K", _i64), ("lda", _i64), ("ldb", _i64), ("ldo", _i64),
+                ("ldr", _i64), ("ld_aux", _i64), ("a_mn_major", _i32), ("b_mn_major", _i32), ("act", _i32),
+                ("out_fp32", _i32), ("alpha", _f32), ("dropout_p", _f32), ("dropout_seed", _u64)]
+
+
+class LayerNormFwdArgs(C.Structure):
+    _fields_ = [("x", _vp), ("gamma", _vp), ("beta", _vp), ("y", _vp), ("mean", _vp), ("rstd", _vp), ("rows", _i64),
+                ("D", _i64), ("ldx", _i64), ("ldy", _i64), ("eps", _f32)]
+
+
+class LayerNormBwdArgs(C.Structure):
+    _fields_ = [("dy", _vp), ("x", _vp), ("gamma", _vp), ("mean", _vp), ("rstd", _vp), ("dx", _vp), ("dgamma", _vp),
+                ("dbeta", _vp), ("rows", _i64), ("D", _i64), ("ld", _i64)]
+
+
+class AttnFwdArgs(C.Structure):
+    _fields_ = [("q", _vp), ("k", _vp), ("v", _vp), ("o", _vp), ("lse", _vp), ("mask", _vp), ("tile_flags", _vp),
+                ("B", _i64), ("H", _i64), ("Lq", _i64), ("Lk", _i64),
+                ("q_sb", _i64), ("q_ss", _i64), ("q_sh", _i64), ("k_sb", _i64), ("k_ss", _i64), ("k_sh", _i64),
+                ("v_sb", _i64), ("v_ss", _i64), ("v_sh", _i64), ("o_sb", _i64), ("o_ss", _i64), ("o_sh", _i64),
+                ("mask_words", _i32), ("scale", _f32), ("dropout_p", _f32), ("dropout_seed", _u64)]
+
+
+class AttnBwdArgs(C.Structure):
+    _fields_ = [("q", _vp), ("k", _vp), ("v", _vp), ("o", _vp), ("d_o", _vp), ("lse", _vp), ("delta", _vp),
+                ("dq", _vp), ("dk", _vp), ("dv", _vp), ("mask", _vp), ("tile_flags", _vp),
+                ("B", _i64), ("H", _i64), ("Lq", _i64), ("Lk", _i64),
+                ("q_sb", _i64), ("q_ss", _i64), ("q_sh", _i64), ("k_sb", _i64), ("k_ss", _i64), ("k_sh", _i64),
+                ("v_sb", _i64), ("v_ss", _i64), ("v_sh", _i64), ("o_sb", _i64), ("o_ss", _i64), ("o_sh", _i64),
+                ("do_sb", _i64), ("do_ss", _i64), ("do_sh", _i64),
+                ("dq_sb", _i64), ("dq_ss", _i64), ("dq_sh", _i64), ("dk_sb", _i64), ("dk_ss", _i64), ("dk_sh", _i64),
+                ("dv_sb", _i64), ("dv_ss", _i64), ("dv_sh", _i64),
+                ("mask_words", _i32), ("scale", _f32), ("dropout_p", _f32), ("dropout_seed", _u64)]
+
+
+class AdamWArgs(C.Structure):
+    _fields_ = [("p", _vp), ("g", _vp), ("m", _vp), ("v", _vp), ("n", _i64), ("sumsq", _vp), ("lr", _vp),
+                ("step", _vp), ("beta1", _f32), ("beta2", _f32), ("eps", _f32), ("weight_decay", _f32),
+                ("max_norm", _f32), ("grad_scale", _f32), ("zero_grad", _i32)]
+
+
+EXPORTS = [
+    "dvla_version", "dvla_last_error", "dvla_launch_count", "dvla_gemm", "dvla_layernorm_fwd", "dvla_layernorm_bwd",
+    "dvla_attn_fwd", "dvla_attn_bwd", "dvla_attn_mask_tiles", "dvla_colsum_accum", "dvla_accum_fp32_into_bf16",
+    "dvla_dropout", "dvla_act_bwd", "dvla_mse_loss", "dvla_cosine_loss", "dvla_silog_stats", "dvla_silog_finish",
+    "dvla_sumsq", "dvla_adamw",
+]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -m dreamvla_b200.build` (nvcc, sm_100a). "
+            "dreamvla_b200 has no CPU or PyTorch fallback for its kernels.")
+    lib = C.CDLL(LIB_PATH)
+    lib.dvla_last_error.restype = C.c_char_p
+    lib.dvla_launch_count.restype = C.c_int64
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise RuntimeError(f"{LIB_PATH} does not export {name}")
+    _lib = lib
+    return lib
+
+
+def launch_count() -> int:
+    return int(load().dvla_launch_count())
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed ({rc}): {load().dvla_last_error().decode()}")
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("dreamvla_b200 kernels need CUDA tensors (no CPU fallback)")
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# raw op wrappers (no autograd)
+# ----------------------------------------------------------------------------------------------------------------------
+def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, act=0, residual=None, aux_out=None, aux_in=None, out=None,
+         out_dtype=torch.bfloat16, alpha=1.0, dropout_p=0.0, dropout_seed=0):
+    """out[M,N] = epi(alpha * A @ B^T).  a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N] if b_mn); 2-D, unit inner stride."""
+    _need_cuda(a, b)
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1, (a.shape, a.stride(), b.shape, b.stride())
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
+    assert K == Kb, f"contraction mismatch {K} vs {Kb}"
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=out_dtype)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    args = GemmArgs()
+    args.a, args.b, args.out = a.data_ptr(), b.data_ptr(), out.data_ptr()
+    args.bias = _ptr(bias)
+    if residual is not None:
+        assert residual.shape == (M, N) and residual.stride(1) == 1 and residual.dtype == out.dtype
+        args.residual, args.ldr = residual.data_ptr(), residual.stride(0)
+    if aux_out is not None:
+        assert aux_out.shape == (M, N) and aux_out.stride(1) == 1 and aux_out.dtype == torch.bfloat16
+        args.aux_out, args.ld_aux = aux_out.data_ptr(), aux_out.stride(0)
+    if aux_in is not None:
+        assert aux_in.shape == (M, N) and aux_in.stride(1) == 1 and aux_in.dtype == torch.bfloat16
+        args.aux_in, args.ld_aux = aux_in.data_ptr(), aux_in.stride(0)
+    args.M, args.N, args.K = M, N, K
+    args.lda, args.ldb, args.ldo = a.stride(0), b.stride(0), out.stride(0)
+    args.a_mn_major, args.b_mn_major = int(a_mn), int(b_mn)
+    args.act = int(act)
+    args.out_fp32 = int(out.dtype == torch.float32)
+    args.alpha = float(alpha)
+    args.dropout_p = float(dropout_p)
+    args.dropout_seed = int(dropout_seed)
+    _check(load().dvla_gemm(C.byref(args), _stream()), "dvla_gemm")
+    return out
+
+
+def layernorm_fwd(x2d, gamma, beta, eps, save_stats=True):
+    _need_cuda(x2d)
+    rows, D = x2d.shape
+    assert x2d.stride(1) == 1 and x2d.dtype == torch.bfloat16
+    y = torch.empty((rows, D), device=x2d.device, dtype=torch.bfloat16)
+    mean = torch.empty(rows, device=x2d.device, dtype=torch.float32) if save_stats else None
+    rstd = torch.empty(rows, device=x2d.device, dtype=torch.float32) if save_stats else None
+    a = LayerNormFwdArgs(x2d.data_ptr(), _ptr(gamma), _ptr(beta), y.data_ptr(), _ptr(mean), _ptr(rstd), rows, D,
+                         x2d.stride(0), y.stride(0), float(eps))
+    _check(load().dvla_layernorm_fwd(C.byref(a), _stream()), "dvla_layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy2d, x2d, gamma, mean, rstd, dgamma_f32, dbeta_f32):
+    rows, D = x2d.shape
+    assert dy2d.is_contiguous() and x2d.is_contiguous()
+    dx = torch.empty_like(x2d)
+    a = LayerNormBwdArgs(dy2d.data_ptr(), x2d.data_ptr(), _ptr(gamma), mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
+                         _ptr(dgamma_f32), _ptr(dbeta_f32), rows, D, D)
+    _check(load().dvla_layernorm_bwd(C.byref(a), _stream()), "dvla_layernorm_bwd")
+    return dx
+
+
+def _bsh(t):
+    """[B, L, H, 64] view -> (batch, seq, head) element strides."""
+    assert t.dim() == 4 and t.shape[-1] == 64 and t.stride(3) == 1 and t.dtype == torch.bfloat16, (t.shape, t.stride())
+    return t.stride(0), t.stride(1), t.stride(2)
+
+
+def attn_fwd(q, k, v, scale, mask_bits=None, tile_flags=None, dropout_p=0.0, dropout_seed=0, need_lse=True):
+    """q [B,Lq,H,64], k/v [B,Lk,H,64] (arbitrary batch/seq/head strides) -> o [B,Lq,H,64] contiguous, lse [B,H,Lq]."""
+    _need_cuda(q, k, v)
+    B, Lq, H, _ = q.shape
+    Lk = k.shape[1]
+    o = torch.empty((B, Lq, H, 64), device=q.device, dtype=torch.bfloat16)
+    lse = torch.empty((B, H, Lq), device=q.device, dtype=torch.float32) if need_lse else None
+    a = AttnFwdArgs()
+    a.q, a.k, a.v, a.o, a.lse = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), _ptr(lse)
+    a.mask, a.tile_flags = _ptr(mask_bits), _ptr(tile_flags)
+    a.B, a.H, a.Lq, a.Lk = B, H, Lq, Lk
+    a.q_sb, a.q_ss, a.q_sh = _bsh(q)
+    a.k_sb, a.k_ss, a.k_sh = _bsh(k)
+    a.v_sb, a.v_ss, a.v_sh = _bsh(v)
+    a.o_sb, a.o_ss, a.o_sh = _bsh(o)
+    a.mask_words = 0 if mask_bits is None else mask_bits.shape[1]
+    a.scale, a.dropout_p, a.dropout_seed = float(scale), float(dropout_p), int(dropout_seed)
+    _check(load().dvla_attn_fwd(C.byref(a), _stream()), "dvla_attn_fwd")
+    return o, lse
+
+
+def attn_bwd(q, k, v, o, d_o, lse, scale, dq, dk, dv, mask_bits=None, tile_flags=None, dropout_p=0.0, dropout_seed=0):
+    B, Lq, H, _ = q.shape
+    Lk = k.shape[1]
+    delta = torch.empty((B, H, Lq), device=q.device, dtype=torch.float32)
+    a = AttnBwdArgs()
+    a.q, a.k, a.v, a.o, a.d_o = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr()
+    a.lse, a.delta = lse.data_ptr(), delta.data_ptr()
+    a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    a.mask, a.tile_flags = _ptr(mask_bits), _ptr(tile_flags)
+    a.B, a.H, a.Lq, a.Lk = B, H, Lq, Lk
+    a.q_sb, a.q_ss, a.q_sh = _bsh(q)
+    a.k_sb, a.k_ss, a.k_sh = _bsh(k)
+    a.v_sb, a.v_ss, a.v_sh = _bsh(v)
+    a.o_sb, a.o_ss, a.o_sh = _bsh(o)
+    a.do_sb, a.do_ss, a.do_sh = _bsh(d_o)
+    a.dq_sb, a.dq_ss, a.dq_sh = _bsh(dq)
+    a.dk_sb, a.dk_ss, a.dk_sh = _bsh(dk)
+    a.dv_sb, a.dv_ss, a.dv_sh = _bsh(dv)
+    a.mask_words = 0 if mask_bits is None else mask_bits.shape[1]
+    a.scale, a.dropout_p, a.dropout_seed = float(scale), float(dropout_p), int(dropout_seed)
+    _check(load().dvla_attn_bwd(C.byref(a), _stream()), "dvla_attn_bwd")
+
+
+def attn_mask_tiles(mask_bits, Lq, Lk):
+    nqt, nkt = (Lq + 63) // 64, (Lk + 63) // 64
+    flags = torch.empty((nqt, nkt), device=mask_bits.device, dtype=torch.uint8)
+    _check(load().dvla_attn_mask_tiles(C.c_void_p(mask_bits.data_ptr()), C.c_int32(mask_bits.shape[1]), _i64(Lq),
+                                       _i64(Lk), C.c_void_p(flags.data_ptr()), _stream()), "dvla_attn_mask_tiles")
+    return flags
+
+
+def colsum_accum(x2d, out_f32):
+    rows, N = x2d.shape
+    assert x2d.stride(1) == 1
+    _check(load().dvla_colsum_accum(C.c_void_p(x2d.data_ptr()), _i64(rows), _i64(N), _i64(x2d.stride(0)),
+                                    C.c_void_p(out_f32.data_ptr()), _stream()), "dvla_colsum_accum")
+
+
+def accum_fp32_into_bf16(src_f32, dst_bf16):
+    assert src_f32.is_contiguous() and dst_bf16.is_contiguous() and src_f32.numel() == dst_bf16.numel()
+    _check(load().dvla_accum_fp32_into_bf16(C.c_void_p(src_f32.data_ptr()), C.c_void_p(dst_bf16.data_ptr()),
+                                            _i64(src_f32.numel()), _stream()), "dvla_accum_fp32_into_bf16")
+
+
+def dropout(x2d, p, seed, out=None):
+    rows, N = x2d.shape
+    assert x2d.stride(1) == 1
+    y = torch.empty((rows, N), device=x2d.device, dtype=torch.bfloat16) if out is None else out
+    _check(load().dvla_dropout(C.c_void_p(x2d.data_ptr()), C.c_void_p(y.data_ptr()), _i64(rows), _i64(N),
+                               _i64(x2d.stride(0)), _i64(y.stride(0)), _f32(p), _u64(seed), _stream()), "dvla_dropout")
+    return y
+
+
+def act_bwd(dy, pre, act):
+    assert dy.is_contiguous() and pre.is_contiguous()
+    dx = torch.empty_like(dy)
+    _check(load().dvla_act_bwd(C.c_void_p(dy.data_ptr()), C.c_void_p(pre.data_ptr()), C.c_void_p(dx.data_ptr()),
+                               _i64(dy.numel()), C.c_int32(act), _stream()), "dvla_act_bwd")
+    return dx
+
+
+def mse_loss(pred2d, label2d, row_mask, weight, loss_out, dpred):
+    rows, Cc = pred2d.shape
+    assert pred2d.is_contiguous() and label2d.is_contiguous()
+    _check(load().dvla_mse_loss(C.c_void_p(pred2d.data_ptr()), C.c_void_p(label2d.data_ptr()),
+                                C.c_void_p(_ptr(row_mask)), _i64(rows), _i64(Cc), _f32(weight),
+                                C.c_void_p(loss_out.data_ptr()), C.c_void_p(_ptr(dpred)), _stream()), "dvla_mse_loss")
+
+
+def cosine_loss(pred2d, label2d, weight, loss_out, dpred):
+    rows, Cc = pred2d.shape
+    assert pred2d.is_contiguous() and label2d.is_contiguous()
+    _check(load().dvla_cosine_loss(C.c_void_p(pred2d.data_ptr()), C.c_void_p(label2d.data_ptr()), _i64(rows), _i64(Cc),
+                                   _f32(weight), C.c_void_p(loss_out.data_ptr()), C.c_void_p(_ptr(dpred)), _stream()),
+           "dvla_cosine_loss")
+
+
+def silog_loss(pred, label, lambd, weight, loss_out, dpred):
+    assert pred.is_contiguous() and label.is_contiguous()
+    n = pred.numel()
+    stats = torch.zeros(2, device=pred.device, dtype=torch.float32)
+    _check(load().dvla_silog_stats(C.c_void_p(pred.data_ptr()), C.c_void_p(label.data_ptr()), _i64(n),
+                                   C.c_void_p(stats.data_ptr()), _stream()), "dvla_silog_stats")
+    _check(load().dvla_silog_finish(C.c_void_p(pred.data_ptr()), C.c_void_p(label.data_ptr()), _i64(n),
+                                    C.c_void_p(stats.data_ptr()), _f32(lambd), _f32(weight),
+                                    C.c_void_p(loss_out.data_ptr()), C.c_void_p(_ptr(dpred)), _stream()),
+           "dvla_silog_finish")
+
+
+def sumsq(g_bf16, out_f32):
+    _check(load().dvla_sumsq(C.c_void_p(g_bf16.data_ptr()), _i64(g_bf16.numel()), C.c_void_p(out_f32.data_ptr()),
+                             _stream()), "dvla_sumsq")
+
+
+def adamw(p, g, m, v, *, sumsq_t, lr_t, step_t, beta1, beta2, eps, weight_decay, max_norm, grad_scale=1.0,
+          zero_grad=True):
+    a = AdamWArgs(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), _ptr(sumsq_t), lr_t.data_ptr(),
+                  step_t.data_ptr(), beta1, beta2, eps, weight_decay, max_norm, grad_scale, int(zero_grad))
+    _check(load().dvla_adamw(C.byref(a), _stream()), "dvla_adamw")

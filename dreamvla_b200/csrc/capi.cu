@@ -1,0 +1,105 @@
+// extern "C" entry points of libdvla_sm100.so (declared in include/dvla.h): argument validation, error text,
+// launch accounting.  No torch types cross this boundary.
+#include <atomic>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "../../include/dvla.h"
+#include "common.cuh"
+
+namespace dvla {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+int gemm_dispatch(const dvla_gemm_args* a, cudaStream_t stream);
+int layernorm_fwd_dispatch(const dvla_layernorm_fwd_args* a, cudaStream_t stream);
+int layernorm_bwd_dispatch(const dvla_layernorm_bwd_args* a, cudaStream_t stream);
+int attn_fwd_dispatch(const dvla_attn_fwd_args* a, cudaStream_t stream);
+int attn_bwd_dispatch(const dvla_attn_bwd_args* a, cudaStream_t stream);
+int attn_mask_tiles_dispatch(const uint32_t* mask, int32_t mask_words, int64_t Lq, int64_t Lk, uint8_t* flags,
+                             cudaStream_t stream);
+int colsum_accum_dispatch(const void* x, int64_t rows, int64_t N, int64_t ld, float* out, cudaStream_t s);
+int accum_fp32_into_bf16_dispatch(const float* src, void* dst, int64_t n, cudaStream_t s);
+int dropout_dispatch(const void* x, void* y, int64_t rows, int64_t N, int64_t ldx, int64_t ldy, float p, uint64_t seed,
+                     cudaStream_t s);
+int act_bwd_dispatch(const void* dy, const void* pre, void* dx, int64_t n, int32_t act, cudaStream_t s);
+int mse_loss_dispatch(const void* pred, const void* label, const float* row_mask, int64_t rows, int64_t C, float weight,
+                      float* loss_out, void* dpred, cudaStream_t s);
+int cosine_loss_dispatch(const void* pred, const void* label, int64_t rows, int64_t C, float weight, float* loss_out,
+                         void* dpred, cudaStream_t s);
+int silog_stats_dispatch(const void* pred, const void* label, int64_t n, float* stats, cudaStream_t s);
+int silog_finish_dispatch(const void* pred, const void* label, int64_t n, const float* stats, float lambd, float weight,
+                          float* loss_out, void* dpred, cudaStream_t s);
+int sumsq_dispatch(const void* g, int64_t n, float* out, cudaStream_t s);
+int adamw_dispatch(const dvla_adamw_args* a, cudaStream_t s);
+
+}  // namespace dvla
+
+using namespace dvla;
+#define S(stream) reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" {
+
+int dvla_version(void) { return 100; }
+const char* dvla_last_error(void) { return g_err; }
+int64_t dvla_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int dvla_gemm(const dvla_gemm_args* args, void* stream) { return gemm_dispatch(args, S(stream)); }
+int dvla_layernorm_fwd(const dvla_layernorm_fwd_args* a, void* stream) { return layernorm_fwd_dispatch(a, S(stream)); }
+int dvla_layernorm_bwd(const dvla_layernorm_bwd_args* a, void* stream) { return layernorm_bwd_dispatch(a, S(stream)); }
+int dvla_attn_fwd(const dvla_attn_fwd_args* a, void* stream) { return attn_fwd_dispatch(a, S(stream)); }
+int dvla_attn_bwd(const dvla_attn_bwd_args* a, void* stream) { return attn_bwd_dispatch(a, S(stream)); }
+int dvla_attn_mask_tiles(const uint32_t* mask, int32_t mask_words, int64_t Lq, int64_t Lk, uint8_t* tile_flags,
+                         void* stream) {
+  return attn_mask_tiles_dispatch(mask, mask_words, Lq, Lk, tile_flags, S(stream));
+}
+int dvla_colsum_accum(const void* x, int64_t rows, int64_t N, int64_t ld, float* out, void* stream) {
+  return colsum_accum_dispatch(x, rows, N, ld, out, S(stream));
+}
+int dvla_accum_fp32_into_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  return accum_fp32_into_bf16_dispatch(src, dst, n, S(stream));
+}
+int dvla_dropout(const void* x, void* y, int64_t rows, int64_t N, int64_t ldx, int64_t ldy, float p, uint64_t seed,
+                 void* stream) {
+  return dropout_dispatch(x, y, rows, N, ldx, ldy, p, seed, S(stream));
+}
+int dvla_act_bwd(const void* dy, const void* pre, void* dx, int64_t n, int32_t act, void* stream) {
+  return act_bwd_dispatch(dy, pre, dx, n, act, S(stream));
+}
+int dvla_mse_loss(const void* pred, const void* label, const float* row_mask, int64_t rows, int64_t C, float weight,
+                  float* loss_out, void* dpred, void* stream) {
+  return mse_loss_dispatch(pred, label, row_mask, rows, C, weight, loss_out, dpred, S(stream));
+}
+int dvla_cosine_loss(const void* pred, const void* label, int64_t rows, int64_t C, float weight, float* loss_out,
+                     void* dpred, void* stream) {
+  return cosine_loss_dispatch(pred, label, rows, C, weight, loss_out, dpred, S(stream));
+}
+int dvla_silog_stats(const void* pred, const void* label, int64_t n, float* stats, void* stream) {
+  return silog_stats_dispatch(pred, label, n, stats, S(stream));
+}
+int dvla_silog_finish(const void* pred, const void* label, int64_t n, const float* stats, float lambd, float weight,
+                      float* loss_out, void* dpred, void* stream) {
+  return silog_finish_dispatch(pred, label, n, stats, lambd, weight, loss_out, dpred, S(stream));
+}
+int dvla_sumsq(const void* g, int64_t n, float* out, void* stream) { return sumsq_dispatch(g, n, out, S(stream)); }
+int dvla_adamw(const dvla_adamw_args* a, void* stream) { return adamw_dispatch(a, S(stream)); }
+
+}  // extern "C"

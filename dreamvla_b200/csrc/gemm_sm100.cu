@@ -1,0 +1,470 @@
+// Persistent, warp-specialised tcgen05 GEMM with fused epilogue for sm_100a.
+//
+//   out[M,N] = epi(alpha * A[M,K] * B[N,K]^T)          bf16 operands, fp32 accumulation in TMEM
+//
+// CTA = 320 threads, one CTA per SM (persistent over output tiles, static round-robin):
+//   warp 0      TMA producer   (one lane): cp.async.bulk.tensor -> 128B-swizzled smem ring (4-6 stages), mbarrier tx
+//   warp 1      MMA issuer     (one lane): tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16 per instruction,
+//                                          tcgen05.commit -> frees smem stage / publishes accumulator
+//   warps 2..9  epilogue       (8 warps) : tcgen05.ld 32x32b.x32 from TMEM -> bias/act/dact/dropout/residual -> global
+// Two accumulator stages in TMEM (2*BN columns) let the epilogue of tile i overlap the mainloop of tile i+1.
+// Both operands may be K-major or MN-major (UMMA descriptor + instruction-descriptor major bits), which covers
+// forward, dgrad and wgrad for nn.Linear ([out,in]) and HF Conv1D ([in,out]) weights without any transpose pass.
+//
+// Replaces the cuBLAS calls behind nn.Linear / Conv1D in the reference (see include/dvla.h for call sites).
+#include "common.cuh"
+#include "../../include/dvla.h"
+
+namespace dvla {
+
+constexpr int BM = 128;
+constexpr int BK = 64;       // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + NUM_EPI_WARPS * 32;
+
+struct GemmParams {
+  void* out;
+  const bf16* bias;
+  const void* residual;
+  bf16* aux_out;
+  const bf16* aux_in;
+  int M, N, K;
+  long long ldo, ldr, ld_aux;
+  int num_m_tiles, num_n_tiles, num_k_blocks;
+  int act, out_fp32, vec_ok;
+  float alpha;
+  float drop_scale;        // 1/(1-p_eff), 0 => dropout disabled
+  uint32_t drop_thresh;    // round(p*65536)
+  uint64_t drop_seed;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;
+};
+
+// ---- epilogue for 8 consecutive columns of one row ---------------------------------------------------------------
+__device__ __forceinline__ void epilogue8(float (&v)[8], int row, int col, const GemmParams& p) {
+  const bool full = p.vec_ok && (col + 8 <= p.N);
+  const int nvalid = min(8, p.N - col);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] *= p.alpha;
+  if (p.bias) {
+    if (full) {
+      uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
+      float2 f;
+      f = unpack_bf16x2(b.x); v[0] += f.x; v[1] += f.y;
+      f = unpack_bf16x2(b.y); v[2] += f.x; v[3] += f.y;
+      f = unpack_bf16x2(b.z); v[4] += f.x; v[5] += f.y;
+      f = unpack_bf16x2(b.w); v[6] += f.x; v[7] += f.y;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nvalid) v[j] += __bfloat162float(p.bias[col + j]);
+    }
+  }
+  if (p.aux_out) {
+    bf16* dst = p.aux_out + static_cast<long long>(row) * p.ld_aux + col;
+    if (full) {
+      uint4 o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                           pack_bf16x2(v[6], v[7]));
+      *reinterpret_cast<uint4*>(dst) = o;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nvalid) dst[j] = __float2bfloat16(v[j]);
+    }
+  }
+  if (p.aux_in) {
+    const bf16* src = p.aux_in + static_cast<long long>(row) * p.ld_aux + col;
+    float x[8];
+    if (full) {
+      uint4 a = __ldg(reinterpret_cast<const uint4*>(src));
+      float2 f;
+      f = unpack_bf16x2(a.x); x[0] = f.x; x[1] = f.y;
+      f = unpack_bf16x2(a.y); x[2] = f.x; x[3] = f.y;
+      f = unpack_bf16x2(a.z); x[4] = f.x; x[5] = f.y;
+      f = unpack_bf16x2(a.w); x[6] = f.x; x[7] = f.y;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = (j < nvalid) ? __bfloat162float(src[j]) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= act_bwd(x[j], p.act);
+  } else if (p.act != ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = act_fwd(v[j], p.act);
+  }
+  if (p.drop_scale != 0.f) {
+    // element index = row*N + col; 8-element RNG blocks need col%8==0 alignment relative to row*N -> use (row*N+col)/8
+    // only when N%8==0, otherwise fall back to per-row block indexing (row*ceil(N/8) + col/8).
+    const uint64_t blk = static_cast<uint64_t>(row) * static_cast<uint64_t>((p.N + 7) >> 3) + (col >> 3);
+    const uint32_t keep = dropout_keep8(p.drop_seed, blk, p.drop_thresh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * p.drop_scale : 0.f;
+  }
+  if (p.out_fp32) {
+    float* dst = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col;
+    if (p.residual) {
+      const float* r = reinterpret_cast<const float*>(p.residual) + static_cast<long long>(row) * p.ldr + col;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nvalid) v[j] += r[j];
+    }
+    if (full) {
+      reinterpret_cast<float4*>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
+      reinterpret_cast<float4*>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nvalid) dst[j] = v[j];
+    }
+  } else {
+    bf16* dst = reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row) * p.ldo + col;
+    if (p.residual) {
+      const bf16* r = reinterpret_cast<const bf16*>(p.residual) + static_cast<long long>(row) * p.ldr + col;
+      if (full) {
+        uint4 a = *reinterpret_cast<const uint4*>(r);
+        float2 f;
+        f = unpack_bf16x2(a.x); v[0] += f.x; v[1] += f.y;
+        f = unpack_bf16x2(a.y); v[2] += f.x; v[3] += f.y;
+        f = unpack_bf16x2(a.z); v[4] += f.x; v[5] += f.y;
+        f = unpack_bf16x2(a.w); v[6] += f.x; v[7] += f.y;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < nvalid) v[j] += __bfloat162float(r[j]);
+      }
+    }
+    if (full) {
+      uint4 o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                           pack_bf16x2(v[6], v[7]));
+      *reinterpret_cast<uint4*>(dst) = o;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nvalid) dst[j] = __float2bfloat16(v[j]);
+    }
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer ------------------------------------------------
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile % p.num_m_tiles) * BM;
+        const int n0 = (tile / p.num_m_tiles) * BN;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          uint8_t* a_dst = sA + s * Cfg::A_BYTES;
+          uint8_t* b_dst = sB + s * Cfg::B_BYTES;
+          if (!A_MN) {
+            tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i) tma_load_2d(a_dst + i * (BK * 128), &tmA, &full_bar[s], m0 + i * 64, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(b_dst, &tmB, &full_bar[s], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i) tma_load_2d(b_dst + i * (BK * 128), &tmB, &full_bar[s], n0 + i * 64, kb * BK);
+          }
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer --------------------------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      int s = 0;
+      uint32_t ph = 0;
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + s * Cfg::A_BYTES);
+          const uint32_t b_base = smem_u32(sB + s * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t a_desc = A_MN ? make_smem_desc_sw128(a_base + k * (UMMA_K * 128), BK * 128, 1024)
+                                         : make_smem_desc_sw128(a_base + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t b_desc = B_MN ? make_smem_desc_sw128(b_base + k * (UMMA_K * 128), BK * 128, 1024)
+                                         : make_smem_desc_sw128(b_base + k * (UMMA_K * 2), 16, 1024);
+            umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_ph ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue ----------------------------------------------------
+    const int q = warp & 3;              // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;    // which half of the BN columns
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile % p.num_m_tiles) * BM;
+      const int n0 = (tile / p.num_m_tiles) * BN;
+      mbar_wait(&tfull_bar[acc], acc_ph);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      constexpr int CHUNKS = BN / 2 / 32;
+#pragma unroll 1
+      for (int ci = 0; ci < CHUNKS; ++ci) {
+        const int c = half * (BN / 2) + ci * 32;
+        uint32_t r[32];
+        tmem_ld_32x32(t_lane + c, r);
+        tmem_ld_wait();
+        if (ci == CHUNKS - 1) {  // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        if (row < p.M) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = n0 + c + g * 8;
+            if (col < p.N) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+              epilogue8(v, row, col, p);
+            }
+          }
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_ph ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ---- SIMT kernel of identical semantics for operands TMA cannot address (unaligned strides, K or N < 8) ------------
+__global__ void gemm_simt_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, long long lda, long long ldb,
+                                 int a_mn, int b_mn, GemmParams p) {
+  // one warp per output element group of 8 columns? keep it simple: one thread per (row, 8-col group), k loop.
+  const long long groups_n = (p.N + 7) / 8;
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<long long>(p.M) * groups_n) return;
+  const int row = static_cast<int>(gid / groups_n);
+  const int col = static_cast<int>(gid % groups_n) * 8;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  const int nvalid = min(8, p.N - col);
+  for (int k = 0; k < p.K; ++k) {
+    const float av = __bfloat162float(a_mn ? a[static_cast<long long>(k) * lda + row] : a[static_cast<long long>(row) * lda + k]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < nvalid) {
+        const int n = col + j;
+        const float bv = __bfloat162float(b_mn ? b[static_cast<long long>(k) * ldb + n] : b[static_cast<long long>(n) * ldb + k]);
+        v[j] = fmaf(av, bv, v[j]);
+      }
+    }
+  }
+  epilogue8(v, row, col, p);
+}
+
+}  // namespace dvla
+
+// ============================================== host side ========================================================
+#include <mutex>
+#include <stdio.h>
+#include <string.h>
+
+namespace dvla {
+void set_error(const char* fmt, ...);
+void count_launch();
+int num_sms();
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor map: inner dim contiguous, 128B swizzle, zero OOB fill.
+bool make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                       uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not found"); return false; }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu ld=%llu box=%ux%u base=%p", (int)r,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld_elems, box_inner, box_outer,
+              base);
+    return false;
+  }
+  return true;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_tc(const dvla_gemm_args* a, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap tmA, tmB;
+  if (!A_MN) { if (!make_tmap_2d_bf16(&tmA, a->a, a->K, a->M, a->lda, BK, BM)) return DVLA_ERR_CUDA; }
+  else       { if (!make_tmap_2d_bf16(&tmA, a->a, a->M, a->K, a->lda, 64, BK)) return DVLA_ERR_CUDA; }
+  if (!B_MN) { if (!make_tmap_2d_bf16(&tmB, a->b, a->K, a->N, a->ldb, BK, BN)) return DVLA_ERR_CUDA; }
+  else       { if (!make_tmap_2d_bf16(&tmB, a->b, a->N, a->K, a->ldb, 64, BK)) return DVLA_ERR_CUDA; }
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return DVLA_ERR_CUDA; }
+    attr_set = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("gemm_tcgen05 launch: %s", cudaGetErrorString(e)); return DVLA_ERR_CUDA; }
+  count_launch();
+  return DVLA_OK;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int gemm_dispatch(const dvla_gemm_args* a, cudaStream_t stream) {
+  if (!a || !a->a || !a->b || !a->out) { set_error("dvla_gemm: null pointer"); return DVLA_ERR_INVALID; }
+  if (a->M <= 0 || a->N <= 0 || a->K <= 0) { set_error("dvla_gemm: non-positive dims M=%lld N=%lld K=%lld", (long long)a->M, (long long)a->N, (long long)a->K); return DVLA_ERR_INVALID; }
+  if (a->aux_in && a->aux_out) { set_error("dvla_gemm: aux_in and aux_out are exclusive"); return DVLA_ERR_INVALID; }
+  if (a->dropout_p < 0.f || a->dropout_p >= 1.f) { set_error("dvla_gemm: dropout_p out of range"); return DVLA_ERR_INVALID; }
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.out = a->out; p.bias = (const bf16*)a->bias; p.residual = a->residual;
+  p.aux_out = (bf16*)a->aux_out; p.aux_in = (const bf16*)a->aux_in;
+  p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K;
+  p.ldo = a->ldo; p.ldr = a->ldr; p.ld_aux = a->ld_aux;
+  p.act = a->act; p.out_fp32 = a->out_fp32; p.alpha = a->alpha;
+  if (a->dropout_p > 0.f) {
+    p.drop_thresh = (uint32_t)(a->dropout_p * 65536.0f + 0.5f);
+    p.drop_scale = 1.0f / (1.0f - (float)p.drop_thresh / 65536.0f);
+    p.drop_seed = a->dropout_seed;
+  }
+  const int oal = a->out_fp32 ? 4 : 8;
+  p.vec_ok = aligned16(a->out) && (a->ldo % oal == 0) &&
+             (!a->bias || aligned16(a->bias)) &&
+             (!a->residual || (aligned16(a->residual) && a->ldr % oal == 0)) &&
+             (!a->aux_out || (aligned16(a->aux_out) && a->ld_aux % 8 == 0)) &&
+             (!a->aux_in || (aligned16(a->aux_in) && a->ld_aux % 8 == 0));
+  p.num_m_tiles = (p.M + BM - 1) / BM;
+  p.num_k_blocks = (p.K + BK - 1) / BK;
+
+  const bool tma_ok = aligned16(a->a) && aligned16(a->b) && (a->lda % 8 == 0) && (a->ldb % 8 == 0);
+  if (!tma_ok) {
+    const long long groups = (long long)p.M * ((p.N + 7) / 8);
+    const int threads = 128;
+    const long long blocks = (groups + threads - 1) / threads;
+    gemm_simt_kernel<<<(unsigned)blocks, threads, 0, stream>>>((const bf16*)a->a, (const bf16*)a->b, a->lda, a->ldb,
+                                                             a->a_mn_major, a->b_mn_major, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("gemm_simt launch: %s", cudaGetErrorString(e)); return DVLA_ERR_CUDA; }
+    count_launch();
+    return DVLA_OK;
+  }
+  // tile-width heuristic: fewer, fatter tiles unless that leaves SMs idle for a whole extra wave
+  const int sms = num_sms();
+  const long long t128 = (long long)p.num_m_tiles * ((p.N + 127) / 128);
+  const long long t256 = (long long)p.num_m_tiles * ((p.N + 255) / 256);
+  const long long cost128 = (t128 + sms - 1) / sms;
+  const long long cost256 = 2 * ((t256 + sms - 1) / sms);
+  const bool use256 = (p.N > 128) && (cost256 <= cost128);
+  const int BNsel = use256 ? 256 : 128;
+  p.num_n_tiles = (p.N + BNsel - 1) / BNsel;
+  const int key = (use256 ? 4 : 0) | (a->a_mn_major ? 2 : 0) | (a->b_mn_major ? 1 : 0);
+  switch (key) {
+    case 0: return launch_tc<128, false, false>(a, p, stream);
+    case 1: return launch_tc<128, false, true>(a, p, stream);
+    case 2: return launch_tc<128, true, false>(a, p, stream);
+    case 3: return launch_tc<128, true, true>(a, p, stream);
+    case 4: return launch_tc<256, false, false>(a, p, stream);
+    case 5: return launch_tc<256, false, true>(a, p, stream);
+    case 6: return launch_tc<256, true, false>(a, p, stream);
+    default: return launch_tc<256, true, true>(a, p, stream);
+  }
+}
+
+}  // namespace dvla

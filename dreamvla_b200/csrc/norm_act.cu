@@ -1,0 +1,333 @@
+// HBM-bound row kernels: LayerNorm fwd/bwd, column sums (bias grads), dropout, activation backward, fp32->bf16 folds.
+// One warp per row, 16-byte vector accesses, grids sized against the SM count.
+#include "common.cuh"
+#include "../../include/dvla.h"
+
+namespace dvla {
+void set_error(const char* fmt, ...);
+void count_launch();
+int num_sms();
+
+#define DVLA_CHECK_LAUNCH(name)                                                                 \
+  do {                                                                                          \
+    cudaError_t e__ = cudaGetLastError();                                                       \
+    if (e__ != cudaSuccess) { set_error("%s launch: %s", name, cudaGetErrorString(e__)); return DVLA_ERR_CUDA; } \
+    count_launch();                                                                             \
+  } while (0)
+
+__device__ __forceinline__ void load8(const bf16* p, float (&f)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 t;
+  t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
+  *reinterpret_cast<uint4*>(p) =
+      make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// LayerNorm forward: warp per row; row cached in registers (D <= 1024) => one HBM read + one write per element.
+// ------------------------------------------------------------------------------------------------------------------
+template <int NV>  // NV = ceil(D / 256): 16-byte vectors per lane
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamma,
+                                                            const bf16* __restrict__ beta, bf16* __restrict__ y,
+                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                            long long rows, int D, long long ldx, long long ldy, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = D >> 3;
+  for (long long row = static_cast<long long>(blockIdx.x) * 8 + warp; row < rows; row += static_cast<long long>(gridDim.x) * 8) {
+    const bf16* xr = x + row * ldx;
+    float v[NV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        load8(xr + vi * 8, v[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[i][j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+      }
+    }
+    const float mean = warp_sum(s) / D;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; ss += d * d; }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / D + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+    bf16* yr = y + row * ldy;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        float o[8];
+        float gm[8], bt[8];
+        if (gamma) load8(gamma + vi * 8, gm);
+        if (beta) load8(beta + vi * 8, bt);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float t = (v[i][j] - mean) * rstd;
+          if (gamma) t *= gm[j];
+          if (beta) t += bt[j];
+          o[j] = t;
+        }
+        store8(yr + vi * 8, o);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// LayerNorm backward: warp per row for dx; per-lane register partials for dgamma/dbeta, folded through shared memory
+// and one fp32 atomicAdd per column per CTA.
+// ------------------------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                            const bf16* __restrict__ gamma, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, bf16* __restrict__ dx,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                            long long rows, int D, long long ld) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = D >> 3;
+  float pg[NV][8], pb[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { pg[i][j] = 0.f; pb[i][j] = 0.f; }
+
+  for (long long row = static_cast<long long>(blockIdx.x) * 8 + warp; row < rows; row += static_cast<long long>(gridDim.x) * 8) {
+    const float mu = mean[row], rs = rstd[row];
+    float xh[NV][8], gdy[NV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        float xv[8], dv[8], gm[8];
+        load8(x + row * ld + vi * 8, xv);
+        load8(dy + row * ld + vi * 8, dv);
+        if (gamma) load8(gamma + vi * 8, gm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float h = (xv[j] - mu) * rs;
+          xh[i][j] = h;
+          pg[i][j] += dv[j] * h;
+          pb[i][j] += dv[j];
+          const float gd = gamma ? dv[j] * gm[j] : dv[j];
+          gdy[i][j] = gd;
+          s1 += gd;
+          s2 += gd * h;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { xh[i][j] = 0.f; gdy[i][j] = 0.f; }
+      }
+    }
+    s1 = warp_sum(s1) / D;
+    s2 = warp_sum(s2) / D;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rs * (gdy[i][j] - s1 - xh[i][j] * s2);
+        store8(dx + row * ld + vi * 8, o);
+      }
+    }
+  }
+  if (dgamma || dbeta) {
+    __shared__ float red[8][32 * 8 + 1];
+    for (int pass = 0; pass < 2; ++pass) {
+      float* dst = pass == 0 ? dgamma : dbeta;
+      if (!dst) continue;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = pass == 0 ? pg[i][j] : pb[i][j];
+        __syncthreads();
+        // 256 threads fold 8 warps for the 256 columns of this vector slab
+        const int colv = threadIdx.x;  // 0..255 -> lane*8+j
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][colv];
+        const int col = (colv >> 3) * 8 + i * 256 + (colv & 7);
+        if (col < D) atomicAdd(dst + col, t);
+      }
+    }
+  }
+}
+
+int layernorm_fwd_dispatch(const dvla_layernorm_fwd_args* a, cudaStream_t stream) {
+  if (!a || !a->x || !a->y) { set_error("layernorm_fwd: null pointer"); return DVLA_ERR_INVALID; }
+  if (a->D % 8 || a->ldx % 8 || a->ldy % 8 || a->D > 1024 || a->D <= 0) {
+    set_error("layernorm_fwd: need D%%8==0, D<=1024, strides%%8==0 (D=%lld)", (long long)a->D);
+    return DVLA_ERR_UNSUPPORTED;
+  }
+  if (a->rows <= 0) return DVLA_OK;
+  const int nv = (int)((a->D + 255) / 256);
+  long long blocks = (a->rows + 7) / 8;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+#define LN_FWD(NV) layernorm_fwd_kernel<NV><<<(unsigned)blocks, 256, 0, stream>>>((const bf16*)a->x, (const bf16*)a->gamma, \
+      (const bf16*)a->beta, (bf16*)a->y, a->mean, a->rstd, a->rows, (int)a->D, a->ldx, a->ldy, a->eps)
+  switch (nv) { case 1: LN_FWD(1); break; case 2: LN_FWD(2); break; case 3: LN_FWD(3); break; default: LN_FWD(4); break; }
+#undef LN_FWD
+  DVLA_CHECK_LAUNCH("layernorm_fwd");
+  return DVLA_OK;
+}
+
+int layernorm_bwd_dispatch(const dvla_layernorm_bwd_args* a, cudaStream_t stream) {
+  if (!a || !a->dy || !a->x || !a->mean || !a->rstd || !a->dx) { set_error("layernorm_bwd: null pointer"); return DVLA_ERR_INVALID; }
+  if (a->D % 8 || a->ld % 8 || a->D > 1024 || a->D <= 0) {
+    set_error("layernorm_bwd: need D%%8==0, D<=1024, ld%%8==0 (D=%lld)", (long long)a->D);
+    return DVLA_ERR_UNSUPPORTED;
+  }
+  if (a->rows <= 0) return DVLA_OK;
+  const int nv = (int)((a->D + 255) / 256);
+  long long blocks = (a->rows + 7) / 8;
+  const long long cap = (long long)num_sms() * 2;
+  if (blocks > cap) blocks = cap;
+#define LN_BWD(NV) layernorm_bwd_kernel<NV><<<(unsigned)blocks, 256, 0, stream>>>((const bf16*)a->dy, (const bf16*)a->x, \
+      (const bf16*)a->gamma, a->mean, a->rstd, (bf16*)a->dx, a->dgamma, a->dbeta, a->rows, (int)a->D, a->ld)
+  switch (nv) { case 1: LN_BWD(1); break; case 2: LN_BWD(2); break; case 3: LN_BWD(3); break; default: LN_BWD(4); break; }
+#undef LN_BWD
+  DVLA_CHECK_LAUNCH("layernorm_bwd");
+  return DVLA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Column sum (bias gradient): out[n] += sum_r x[r, n]
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) colsum_kernel(const bf16* __restrict__ x, long long rows, int N, long long ld,
+                                                     float* __restrict__ out, int rows_per_block, int vec) {
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  if (vec) {
+    const int cg = blockIdx.x * blockDim.x + threadIdx.x;  // 8-column group
+    if (cg * 8 >= N) return;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long r = r0; r < r1; ++r) {
+      float f[8];
+      load8(x + r * ld + cg * 8, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(out + cg * 8 + j, acc[j]);
+  } else {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    float acc = 0.f;
+    for (long long r = r0; r < r1; ++r) acc += __bfloat162float(x[r * ld + c]);
+    atomicAdd(out + c, acc);
+  }
+}
+int colsum_accum_dispatch(const void* x, int64_t rows, int64_t N, int64_t ld, float* out, cudaStream_t s) {
+  if (!x || !out) { set_error("colsum: null pointer"); return DVLA_ERR_INVALID; }
+  if (rows <= 0 || N <= 0) return DVLA_OK;
+  const int vec = (N % 8 == 0) && (ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  const long long cols = vec ? N / 8 : N;
+  const int bx = (int)((cols + 127) / 128);
+  int by = (int)((2LL * num_sms() + bx - 1) / bx);
+  if (by > rows) by = (int)rows;
+  if (by < 1) by = 1;
+  const int rpb = (int)((rows + by - 1) / by);
+  by = (int)((rows + rpb - 1) / rpb);
+  colsum_kernel<<<dim3(bx, by), 128, 0, s>>>((const bf16*)x, rows, (int)N, ld, out, rpb, vec);
+  DVLA_CHECK_LAUNCH("colsum");
+  return DVLA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void accum_fp32_into_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dst[i] = __float2bfloat16(__bfloat162float(dst[i]) + src[i]);
+}
+int accum_fp32_into_bf16_dispatch(const float* src, void* dst, int64_t n, cudaStream_t s) {
+  if (!src || !dst) { set_error("accum_fp32_into_bf16: null pointer"); return DVLA_ERR_INVALID; }
+  if (n <= 0) return DVLA_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();
+  accum_fp32_into_bf16_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, (bf16*)dst, n);
+  DVLA_CHECK_LAUNCH("accum_fp32_into_bf16");
+  return DVLA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Dropout with the GEMM-epilogue mask convention: RNG block = row*ceil(N/8) + col/8, bit col%8.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void dropout_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long rows, int N, long long ldx,
+                               long long ldy, uint32_t thresh, float scale, uint64_t seed, int vec) {
+  const int groups = (N + 7) >> 3;
+  const long long total = rows * groups;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / groups;
+    const int col = static_cast<int>(i % groups) * 8;
+    const uint32_t keep = dropout_keep8(seed, static_cast<uint64_t>(i), thresh);
+    if (vec) {
+      float f[8];
+      load8(x + row * ldx + col, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = ((keep >> j) & 1u) ? f[j] * scale : 0.f;
+      store8(y + row * ldy + col, f);
+    } else {
+      for (int j = 0; j < 8 && col + j < N; ++j) {
+        const float f = __bfloat162float(x[row * ldx + col + j]);
+        y[row * ldy + col + j] = __float2bfloat16(((keep >> j) & 1u) ? f * scale : 0.f);
+      }
+    }
+  }
+}
+int dropout_dispatch(const void* x, void* y, int64_t rows, int64_t N, int64_t ldx, int64_t ldy, float p, uint64_t seed,
+                     cudaStream_t s) {
+  if (!x || !y) { set_error("dropout: null pointer"); return DVLA_ERR_INVALID; }
+  if (p < 0.f || p >= 1.f) { set_error("dropout: p out of range"); return DVLA_ERR_INVALID; }
+  if (rows <= 0 || N <= 0) return DVLA_OK;
+  const uint32_t thresh = (uint32_t)(p * 65536.0f + 0.5f);
+  const float scale = 1.0f / (1.0f - (float)thresh / 65536.0f);
+  const int vec = (N % 8 == 0) && (ldx % 8 == 0) && (ldy % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                  ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+  const long long total = rows * ((N + 7) / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
+  dropout_kernel<<<(unsigned)blocks, 256, 0, s>>>((const bf16*)x, (bf16*)y, rows, (int)N, ldx, ldy, thresh, scale, seed, vec);
+  DVLA_CHECK_LAUNCH("dropout");
+  return DVLA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void act_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ pre, bf16* __restrict__ dx,
+                               long long n, int act) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dx[i] = __float2bfloat16(__bfloat162float(dy[i]) * act_bwd(__bfloat162float(pre[i]), act));
+}
+int act_bwd_dispatch(const void* dy, const void* pre, void* dx, int64_t n, int32_t act, cudaStream_t s) {
+  if (!dy || !pre || !dx) { set_error("act_bwd: null pointer"); return DVLA_ERR_INVALID; }
+  if (n <= 0) return DVLA_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
+  act_bwd_kernel<<<(unsigned)blocks, 256, 0, s>>>((const bf16*)dy, (const bf16*)pre, (bf16*)dx, n, act);
+  DVLA_CHECK_LAUNCH("act_bwd");
+  return DVLA_OK;
+}
+
+}  // namespace dvla

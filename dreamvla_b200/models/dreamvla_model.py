@@ -1,0 +1,541 @@
+"""DreamVLA on sm_100a kernels -- drop-in mirror of reference models/dreamvla_model.py:122-991.
+
+Same constructor kwargs, `forward(image_primary, image_wrist, state, text_token, action=None, track_infos=None,
+action_label=None, mode='train')` -> the same 10-tuple, same parameter names / shapes (state_dict-compatible, incl. HF
+Conv1D [in,out] weights), same attributes read by the entry points (`image_processor`, `clip_model`, `vision_encoder`,
+`perceiver_resampler`, `transformer_backbone`, `*_decoder`, `action_model`, `_init_model_type()`, `sequence_length`).
+
+What differs, by design (B200-first, results identical up to bf16 rounding):
+  * every Linear/LayerNorm/attention runs on libdvla_sm100.so (tcgen05 GEMM with fused bias/act/residual/dropout
+    epilogues, flash attention with the reference's {0,-inf} mask as a bit matrix + tile skipping);
+  * both cameras go through the ViT / resampler in ONE batched call (the reference makes two, :672-673,:716-717);
+  * the ViT patch-token permutation of random_masking(…, 0.0) is skipped (outputs invariant, see vit_mae.py here);
+  * identical sentences are CLIP-encoded once.
+Out of scope (need code/weights that are not in the reference tree): use_dinosiglip, use_gpt2_pretrained,
+use_dpt_head, use_fm.  They raise NotImplementedError.
+"""
+from __future__ import annotations
+
+import os
+from functools import partial
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .. import ops
+from . import clip_text
+from .action_model import ActionModel
+from .gpt2 import GPT2Config, GPT2Model
+from .layers import Block, LayerNorm, Linear
+from .perceiver_resampler import PerceiverResampler
+from .vit_mae import MaskedAutoencoderViT, get_1d_sincos_pos_embed_from_grid, get_2d_sincos_pos_embed  # noqa: F401
+
+
+def generate_attention_mask(K, num_A, num_B, atten_goal, atten_goal_state, atten_only_obs, attn_robot_proprio_state,
+                            mask_l_obs_ratio, num_obs_token, action_pred_steps):
+    """Additive {0,-inf} mask [L, L], L = (num_A + num_B) * K.  Same rules, order of application and np.random call
+    sequence as reference dreamvla_model.py:25-66 (bit-exact, tests/test_mask_cpu.py)."""
+    n = num_A + num_B
+    L = n * K
+    mask = torch.zeros((L, L))
+    ninf = -float("inf")
+    for i in range(K):
+        s = i * n
+        e = s + n
+        mask[s:e, e:] = ninf                      # no attention to later timesteps (:41)
+        mask[:, s + num_A:e] = ninf               # B tokens are never attended to (:44)
+        a0 = s + num_A + num_obs_token            # first action row of this timestep
+        a1 = a0 + action_pred_steps
+        if num_obs_token > 0 and action_pred_steps:
+            mask[a0:a1, s + num_A:s + num_A + num_obs_token] = 0.0     # action rows see own obs/query cols (:48)
+        if num_obs_token > 0 and atten_only_obs and action_pred_steps:
+            mask[a0:a1] = ninf                                          # (:50)
+            mask[a0:a1, s + 2:s + num_A] = 0.0                          # image tokens of the own step (:51)
+            mask[a0:a1, s + num_A:s + num_A + num_obs_token] = 0.0      # (:52)
+            if attn_robot_proprio_state:
+                mask[a0:a1, s + 1:s + 2] = 0.0                          # (:54)
+            if mask_l_obs_ratio > 0:
+                count = int(mask_l_obs_ratio * num_obs_token)
+                selected = np.random.choice(range(num_obs_token), size=count, replace=False)
+                for num in selected:
+                    mask[a0:a1, s + num_A + num] = ninf                 # (:59)
+        if num_obs_token > 0 and atten_goal:
+            if i < K - atten_goal:
+                pe = (i + atten_goal) * n
+                if atten_goal_state:
+                    mask[s + num_A:s + num_A + num_obs_token, pe + 1:pe + 2] = 0.0   # (:64)
+    return mask
+
+
+class _WorldDecoder(nn.Module):
+    """Helper that RUNS one world-knowledge decoder (reference :793-911); it owns no parameters -- the parameters stay
+    on DreamVLA under the reference names."""
+
+    @staticmethod
+    def run(feature, projector, mask_token, pos_emb, blocks, norm, pred, n_groups, n_per, n_mask, hidden, act=None):
+        # feature [B, S, n_tok, D] -> projector -> [B*S*n_groups, n_per, hidden]
+        B, S = feature.shape[:2]
+        emb = projector(feature.reshape(-1, feature.shape[-1])).view(B * S * n_groups, n_per, hidden)
+        mask_tokens = mask_token.expand(B * S * n_groups, n_mask, -1)
+        x = torch.cat((emb, mask_tokens), dim=1) + pos_emb
+        x = blocks(x)
+        x = norm(x[:, -n_mask:, :].reshape(-1, hidden))
+        return pred(x, act=act)
+
+
+class DreamVLA(nn.Module):
+    def __init__(
+        self,
+        finetune_type,
+        clip_device,
+        vit_checkpoint_path,
+        sequence_length=10,
+        num_resampler_query=9,
+        num_obs_token_per_image=10,
+        obs_pred=False,
+        atten_only_obs=False,
+        attn_robot_proprio_state=False,
+        atten_goal=False,
+        atten_goal_state=False,
+        mask_l_obs_ratio=0.0,
+        calvin_input_image_size=224,
+        patch_size=16,
+        mask_ratio=0.0,
+        num_token_per_timestep=41,
+        input_self=False,
+        action_pred_steps=1,
+        transformer_layers=12,
+        hidden_dim=384,
+        transformer_heads=12,
+        phase="",
+        gripper_width=False,
+        pred_num=1,
+        depth_pred=False,
+        trajectory_pred=False,
+        use_depth_query=False,
+        use_dpt_head=False,
+        use_trajectory_query=False,
+        track_label_patch_size=4,
+        dino_feat_pred=False,
+        sam_feat_pred=False,
+        use_dinosiglip=False,
+        use_dit_head=False,
+        use_gpt2_pretrained=False,
+        no_pred_gripper_traj=False,
+        no_unshuffle=False,
+        share_query=False,
+        attn_implementation=False,
+        use_fm=False,
+        dit_type="DiT-B",
+    ):
+        super().__init__()
+        for flag, name in ((use_dinosiglip, "use_dinosiglip"), (use_gpt2_pretrained, "use_gpt2_pretrained"),
+                           (use_dpt_head, "use_dpt_head"), (use_fm, "use_fm")):
+            if flag:
+                raise NotImplementedError(f"{name}: needs weights/code outside the reference tree (out of scope, SURVEY §8a)")
+        self.finetune_type = finetune_type
+        self.device = clip_device
+        self.sequence_length = sequence_length
+        self.action_pred_steps = action_pred_steps
+        self.obs_pred = obs_pred
+        self.depth_pred = depth_pred
+        self.dino_feat_pred = dino_feat_pred
+        self.sam_feat_pred = sam_feat_pred
+        self.trajectory_pred = trajectory_pred
+        self.atten_goal = atten_goal
+        self.atten_goal_state = atten_goal_state
+        self.atten_only_obs = atten_only_obs
+        self.attn_robot_proprio_state = attn_robot_proprio_state
+        self.mask_l_obs_ratio = mask_l_obs_ratio
+        self.hidden_dim = hidden_dim
+        self.phase = phase
+        self.dit_type = dit_type
+        assert self.phase in ["pretrain", "finetune", "evaluate"]
+        self.share_query = share_query
+        self.gripper_width = gripper_width
+        self.vit_checkpoint_path = vit_checkpoint_path
+        self.pred_num = pred_num
+        self.use_dinosiglip = False
+        D = hidden_dim
+
+        self.text_projector = Linear(512, D)
+        self.arm_state_encoder = Linear(6, D)
+        self.gripper_state_encoder = Linear(2, D)
+        self.state_projector = Linear(2 * D, D)
+        # action encoders exist in the reference (:203-205) but are never used in forward
+        self.action_pose_encoder = Linear(6, D)
+        self.action_gripper_position_encoder = Linear(2, D)
+        self.action_projector = Linear(2 * D, D)
+
+        self.vision_encoder = MaskedAutoencoderViT(patch_size=16, embed_dim=768, depth=12, num_heads=12,
+                                                   decoder_embed_dim=512, decoder_depth=8, decoder_num_heads=16,
+                                                   mlp_ratio=4, norm_layer=partial(LayerNorm, eps=1e-6))
+        self.RESAMPLER_hidden_dim = 768
+        self.NUM_RESAMPLER_QUERY = num_resampler_query
+        self.perceiver_resampler = PerceiverResampler(dim=768, num_latents=num_resampler_query, depth=3)
+        self.image_primary_projector = Linear(768, D)
+        self.cls_token_primary_projector = Linear(768, D)
+        self.image_wrist_projector = Linear(768, D)
+        self.cls_token_wrist_projector = Linear(768, D)
+
+        if self.action_pred_steps > 0:
+            self.action_pred_token = nn.Parameter(torch.zeros(1, 1, self.action_pred_steps, D))
+
+        self.NUM_OBS_TOKEN = self.NUM_DEPTH_TOKEN = self.NUM_TRAJ_TOKEN = self.NUM_DINO_TOKEN = self.NUM_SAM_TOKEN = 0
+        if self.obs_pred:
+            self.NUM_OBS_TOKEN_PER_IMAGE = num_obs_token_per_image
+            self.NUM_OBS_TOKEN = num_obs_token_per_image * 2
+            self.obs_tokens = nn.Parameter(torch.zeros(1, 1, self.NUM_OBS_TOKEN, D))
+        if self.depth_pred:
+            self.NUM_OBS_TOKEN_PER_DEPTH = num_obs_token_per_image
+            self.NUM_DEPTH_TOKEN = num_obs_token_per_image * 2
+        if self.dino_feat_pred:
+            self.NUM_OBS_TOKEN_PER_DINO = num_obs_token_per_image
+            self.NUM_DINO_TOKEN = num_obs_token_per_image * 2
+        if self.sam_feat_pred:
+            self.NUM_OBS_TOKEN_PER_SAM = num_obs_token_per_image
+            self.NUM_SAM_TOKEN = num_obs_token_per_image * 2
+        if self.trajectory_pred:
+            self.NUM_OBS_TOKEN_PER_TRAJ = num_obs_token_per_image
+            self.NUM_TRAJ_TOKEN = num_obs_token_per_image * (1 if no_pred_gripper_traj else 2)
+        if not self.share_query:
+            if self.depth_pred:
+                self.depth_tokens = nn.Parameter(torch.zeros(1, 1, self.NUM_DEPTH_TOKEN, D))
+            if self.dino_feat_pred:
+                self.dino_feat_tokens = nn.Parameter(torch.zeros(1, 1, self.NUM_DINO_TOKEN, D))
+            if self.sam_feat_pred:
+                self.sam_feat_tokens = nn.Parameter(torch.zeros(1, 1, self.NUM_SAM_TOKEN, D))
+            if trajectory_pred:
+                self.trajectory_tokens = nn.Parameter(torch.zeros(1, 1, self.NUM_TRAJ_TOKEN, D))
+
+        self.embedding_layer_norm = LayerNorm(D)
+        self.attention_mask = nn.Parameter(self._make_mask(), requires_grad=False)
+        self._mask_cache = None
+        self.transformer_backbone_position_embedding = nn.Parameter(torch.zeros(1, sequence_length, 1, D), requires_grad=True)
+        config = GPT2Config()
+        config.hidden_size = D
+        config.n_layer = transformer_layers
+        config.vocab_size = 1
+        config.n_head = transformer_heads
+        self.attn_implementation = config.attn_implementation = attn_implementation
+        self.transformer_backbone = GPT2Model(config)
+
+        MLP_hidden_dim = D // 2
+        # unused in forward, kept for state_dict compatibility (:320-333)
+        self.recon_state_decoder = nn.Sequential(Linear(D, MLP_hidden_dim), nn.ReLU(), Linear(MLP_hidden_dim, MLP_hidden_dim), nn.ReLU())
+        self.recon_arm_state_decoder = nn.Sequential(Linear(MLP_hidden_dim, 6), nn.Tanh())
+        self.recon_gripper_state_decoder = nn.Sequential(Linear(MLP_hidden_dim, 1), nn.Sigmoid())
+
+        n_patch = int(calvin_input_image_size ** 2 / patch_size / patch_size) * pred_num
+        q_in = int(D / 4) if share_query else D
+
+        def two_blocks():
+            return nn.Sequential(Block(D, num_heads=16, mlp_ratio=4, qkv_bias=True, eps=1e-5),
+                                 Block(D, num_heads=16, mlp_ratio=4, qkv_bias=True, eps=1e-5))
+
+        if self.obs_pred:
+            self.IMAGE_DECODER_hidden_dim = D
+            self.NUM_MASK_TOKEN = n_patch
+            self.PATCH_SIZE = patch_size
+            self.mask_token = nn.Parameter(torch.zeros(1, 1, D))
+            self.image_decoder_obs_pred_projector = Linear(q_in, D)
+            self.image_decoder_position_embedding = nn.Parameter(torch.zeros(1, num_obs_token_per_image + n_patch, D), requires_grad=False)
+            self.image_decoder = two_blocks()
+            self.image_decoder_norm = LayerNorm(D)
+            self.image_decoder_pred = Linear(D, patch_size ** 2 * 3)
+        if self.depth_pred:
+            self.use_dpt_head = False
+            self.DEPTH_DECODER_hidden_dim = D
+            self.NUM_DEPTH_MASK_TOKEN = n_patch
+            self.PATCH_SIZE = patch_size
+            self.depth_decoder_obs_pred_projector = Linear(q_in, D)
+            self.depth_decoder = two_blocks()
+            self.depth_decoder_norm = LayerNorm(D)
+            self.depth_decoder_pred = Linear(D, patch_size ** 2)
+            self.depth_mask_token = nn.Parameter(torch.zeros(1, 1, D))
+            self.depth_decoder_position_embedding = nn.Parameter(torch.zeros(1, num_obs_token_per_image + n_patch, D), requires_grad=False)
+        if self.dino_feat_pred:
+            self.DINO_DECODER_hidden_dim = D
+            self.NUM_DINO_MASK_TOKEN = 256 * pred_num
+            self.dino_decoder_obs_pred_projector = Linear(q_in, D)
+            self.dino_feat_decoder = two_blocks()
+            self.dino_decoder_norm = LayerNorm(D)
+            self.dino_decoder_pred = Linear(D, 768)
+            self.dino_mask_token = nn.Parameter(torch.zeros(1, 1, D))
+            self.dino_decoder_position_embedding = nn.Parameter(torch.zeros(1, num_obs_token_per_image + 256 * pred_num, D), requires_grad=False)
+        if self.sam_feat_pred:
+            self.SAM_DECODER_hidden_dim = D
+            self.NUM_SAM_MASK_TOKEN = 256 * pred_num
+            self.sam_decoder_obs_pred_projector = Linear(q_in, D)
+            self.sam_feat_decoder = two_blocks()
+            self.sam_decoder_norm = LayerNorm(D)
+            self.sam_decoder_pred = Linear(D, 256)
+            self.sam_mask_token = nn.Parameter(torch.zeros(1, 1, D))
+            self.sam_decoder_position_embedding = nn.Parameter(torch.zeros(1, num_obs_token_per_image + 256 * pred_num, D), requires_grad=False)
+        if self.trajectory_pred:
+            self.use_traj_query = use_trajectory_query
+            self.track_label_patch_size = track_label_patch_size
+            self.TRAJ_DECODER_hidden_dim = D
+            if no_unshuffle:
+                self.NUM_TRAJ_MASK_TOKEN = 784 * pred_num
+                self.traj_decoder_pred = Linear(D, 2)
+            else:
+                self.NUM_TRAJ_MASK_TOKEN = n_patch
+                self.traj_decoder_pred = Linear(D, (patch_size // track_label_patch_size) ** 2 * 2)
+            self.PATCH_SIZE = patch_size
+            self.traj_decoder_obs_pred_projector = Linear(D, D)
+            self.traj_decoder = two_blocks()
+            self.traj_decoder_norm = LayerNorm(D)
+            self.traj_mask_token = nn.Parameter(torch.zeros(1, 1, D))
+            torch.nn.init.normal_(self.traj_mask_token, std=0.02)
+            self.traj_decoder_position_embedding = nn.Parameter(torch.zeros(1, num_obs_token_per_image + self.NUM_TRAJ_MASK_TOKEN, D), requires_grad=False)
+
+        self.use_dit_head = use_dit_head
+        if self.use_dit_head:
+            self.action_model = ActionModel(model_type=dit_type, token_size=D, in_channels=7,
+                                            future_action_window_size=self.action_pred_steps - 1, past_action_window_size=0)
+        else:
+            self.action_decoder = nn.Sequential(Linear(D, MLP_hidden_dim), nn.ReLU(), Linear(MLP_hidden_dim, MLP_hidden_dim), nn.ReLU())
+            self.arm_action_decoder = nn.Sequential(Linear(MLP_hidden_dim, 6), nn.Tanh())
+            self.gripper_action_decoder = nn.Sequential(Linear(MLP_hidden_dim, 1), nn.Sigmoid())
+        self.initialize_weights()
+
+        if vit_checkpoint_path is not None and os.path.exists(str(vit_checkpoint_path)):
+            vit_checkpoint = torch.load(vit_checkpoint_path, map_location="cpu")
+            self.vision_encoder.load_state_dict(vit_checkpoint["model"], strict=False)
+        ckpt = "checkpoints/clip/ViT-B-32.pt"
+        self.clip_model, self.image_processor = clip_text.load(ckpt if os.path.exists(ckpt) else "ViT-B/32", device=clip_device)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def _this_num_obs_token(self):
+        if self.share_query:
+            return self.NUM_OBS_TOKEN
+        if self.obs_pred or self.depth_pred or self.trajectory_pred or self.dino_feat_pred or self.sam_feat_pred:
+            return self.NUM_OBS_TOKEN + self.NUM_DEPTH_TOKEN + self.NUM_TRAJ_TOKEN + self.NUM_DINO_TOKEN + self.NUM_SAM_TOKEN
+        return 0
+
+    def _make_mask(self):
+        n_obs = self._this_num_obs_token()
+        return generate_attention_mask(K=self.sequence_length, num_A=1 + 1 + self.NUM_RESAMPLER_QUERY * 2 + 1 * 2,
+                                       num_B=n_obs + self.action_pred_steps, atten_goal=self.atten_goal,
+                                       atten_goal_state=self.atten_goal_state, atten_only_obs=self.atten_only_obs,
+                                       attn_robot_proprio_state=self.attn_robot_proprio_state,
+                                       mask_l_obs_ratio=self.mask_l_obs_ratio, num_obs_token=n_obs,
+                                       action_pred_steps=self.action_pred_steps)
+
+    def _attn_mask(self, device):
+        """Bit-matrix form of self.attention_mask, rebuilt when the parameter changes (pretrain phase / load_state_dict)."""
+        key = (self.attention_mask.data_ptr(), self.attention_mask._version, str(device))
+        if self._mask_cache is None or self._mask_cache[0] != key:
+            self._mask_cache = (key, ops.AttnMask.from_additive(self.attention_mask.detach().float().cpu(), device))
+        return self._mask_cache[1]
+
+    def initialize_weights(self):  # reference :543-579
+        def sincos(dim, n_obs, n_mask):
+            a = get_2d_sincos_pos_embed(dim, int(n_obs ** 0.5), cls_token=False)
+            b = get_2d_sincos_pos_embed(dim, int(n_mask ** 0.5), cls_token=False)
+            return torch.from_numpy(np.concatenate((a, b), axis=0)).float().unsqueeze(0)
+        if self.obs_pred:
+            self.image_decoder_position_embedding.data.copy_(sincos(self.hidden_dim, self.NUM_OBS_TOKEN_PER_IMAGE, self.NUM_MASK_TOKEN))
+            torch.nn.init.normal_(self.mask_token, std=0.02)
+        if self.depth_pred:
+            self.depth_decoder_position_embedding.data.copy_(sincos(self.hidden_dim, self.NUM_OBS_TOKEN_PER_DEPTH, self.NUM_DEPTH_MASK_TOKEN))
+            torch.nn.init.normal_(self.depth_mask_token, std=0.02)
+        # sam: position embedding stays zero and the mask token zero-initialised (reference :558-564 is commented out)
+        if self.dino_feat_pred:
+            self.dino_decoder_position_embedding.data.copy_(sincos(self.hidden_dim, self.NUM_OBS_TOKEN_PER_DINO, self.NUM_DINO_MASK_TOKEN))
+            torch.nn.init.normal_(self.dino_mask_token, std=0.02)
+        if self.trajectory_pred:
+            self.traj_decoder_position_embedding.data.copy_(sincos(self.hidden_dim, self.NUM_OBS_TOKEN_PER_TRAJ, self.NUM_TRAJ_MASK_TOKEN))
+            torch.nn.init.normal_(self.traj_mask_token, std=0.02)
+        torch.nn.init.normal_(self.transformer_backbone_position_embedding, std=0.02)
+        self.apply(self._init_weights)
+
+    def _init_weights(self, m):  # reference :581-591 (Conv1D is not nn.Linear: GPT-2 keeps its own init)
+        if isinstance(m, nn.Linear):
+            torch.nn.init.xavier_uniform_(m.weight)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            if m.weight is not None:
+                nn.init.constant_(m.weight, 1.0)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+
+    def _init_model_type(self):  # reference :593-603
+        self.vision_encoder_type = next(self.vision_encoder.parameters()).type()
+        self.perceiver_resampler_type = next(self.perceiver_resampler.parameters()).type()
+        self.transformer_backbone_type = next(self.transformer_backbone.parameters()).type()
+        if not self.use_dit_head:
+            self.action_decoder_type = next(self.action_decoder.parameters()).type()
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def forward(self, image_primary, image_wrist, state, text_token, action=None, track_infos=None, action_label=None,
+                mode="train", diffusion_noise=None, diffusion_timestep=None, diffusion_drop_ids=None, sample_noise=None):
+        """Reference :609-991.  The four trailing keyword arguments inject the tensors the reference samples inside
+        forward (action_model.py:59-60, models.py:83, dreamvla_model.py:944) so parity tests can line them up."""
+        if self.training and self.phase == "pretrain":       # :610-628 mask regenerated each forward (np.random)
+            self.attention_mask = nn.Parameter(self._make_mask().to(self.attention_mask.device), requires_grad=False)
+        B, S, _ = state.shape
+        D = self.hidden_dim
+        dev = image_primary.device
+        dt = torch.bfloat16
+        image_pred = depth_pred = traj_pred = dino_pred = sam_pred = None
+        arm_pred_action = gripper_pred_action = None
+        arm_pred_state = gripper_pred_state = loss_arm_action = None
+
+        # ---- text (:643-653) ----
+        with torch.no_grad():
+            text_feature = self.clip_model.encode_text(text_token.flatten(0, 1)).to(dt)
+        text_embedding = self.text_projector(text_feature).view(B, S, -1, D)
+
+        # ---- state (:656-664) ----
+        st = state.flatten(0, 1).to(dt)
+        arm_state_feature = self.arm_state_encoder(st[:, :6].contiguous())
+        if not self.gripper_width:
+            idx = torch.where(st[:, 6:].flatten() < 1, 0, 1)
+            gripper_in = F.one_hot(idx, num_classes=2).to(dt)
+        else:
+            gripper_in = st[:, 6:].contiguous()
+        gripper_state_feature = self.gripper_state_encoder(gripper_in)
+        state_embedding = self.state_projector(torch.cat((arm_state_feature, gripper_state_feature), dim=1)).view(B, S, -1, D)
+
+        # ---- vision: both cameras in one batch (:666-673) ----
+        with torch.no_grad():
+            imgs = torch.cat((image_primary.flatten(0, 1), image_wrist.flatten(0, 1)), dim=0).to(dt)
+            feats, _, _ = self.vision_encoder.forward_encoder(imgs, mask_ratio=0.0)        # [2BS, 197, 768]
+        n = B * S
+        cls_tok = feats[:, 0, :]                                                            # [2BS, 768]
+        patches = feats[:, 1:, :]                                                           # [2BS, 196, 768]
+        resampled = self.perceiver_resampler(patches.unsqueeze(1).unsqueeze(1))            # [2BS, 1, nq, 768]
+        resampled = resampled.reshape(2, n * self.NUM_RESAMPLER_QUERY, 768)
+        image_primary_embedding = self.image_primary_projector(resampled[0]).view(B, S, -1, D)
+        image_wrist_embedding = self.image_wrist_projector(resampled[1]).view(B, S, -1, D)
+        cls_p = self.cls_token_primary_projector(cls_tok[:n].contiguous()).view(B, S, -1, D)
+        cls_w = self.cls_token_wrist_projector(cls_tok[n:].contiguous()).view(B, S, -1, D)
+
+        # ---- token assembly (:739-759); slot order is part of the contract ----
+        parts = [text_embedding, state_embedding, image_primary_embedding, image_wrist_embedding, cls_p, cls_w]
+        pred_token_start_idx = 1 + 1 + 2 * self.NUM_RESAMPLER_QUERY + 2
+        if self.obs_pred:
+            parts.append(self.obs_tokens.expand(B, S, -1, -1))
+        if not self.share_query:
+            if self.depth_pred:
+                parts.append(self.depth_tokens.expand(B, S, -1, -1))
+            if self.dino_feat_pred:
+                parts.append(self.dino_feat_tokens.expand(B, S, -1, -1))
+            if self.sam_feat_pred:
+                parts.append(self.sam_feat_tokens.expand(B, S, -1, -1))
+            if self.trajectory_pred:
+                parts.append(self.trajectory_tokens.expand(B, S, -1, -1))
+        if self.action_pred_steps > 0:
+            parts.append(self.action_pred_token.expand(B, S, -1, -1))
+        transformer_input = torch.cat(parts, dim=2)
+        transformer_input = transformer_input + self.transformer_backbone_position_embedding
+        transformer_input = transformer_input.flatten(1, 2)
+
+        # ---- backbone (:765-790) ----
+        transformer_input = self.embedding_layer_norm(transformer_input)
+        transformer_output = self.transformer_backbone(inputs_embeds=transformer_input, attention_mask=self._attn_mask(dev))
+        transformer_output = transformer_output.view(B, S, -1, D)
+
+        # ---- world-knowledge heads (:793-911) ----
+        cur = 0
+        q4 = int(D / 4)
+        P0 = pred_token_start_idx
+        if self.obs_pred and mode == "train":
+            if self.share_query:
+                feat = transformer_output[:, :, P0:P0 + self.NUM_OBS_TOKEN, :q4]
+                cur = 0
+            else:
+                feat = transformer_output[:, :, P0:P0 + self.NUM_OBS_TOKEN, :]
+                cur += self.NUM_OBS_TOKEN
+            g = self.NUM_OBS_TOKEN // self.NUM_OBS_TOKEN_PER_IMAGE
+            out = _WorldDecoder.run(feat, self.image_decoder_obs_pred_projector, self.mask_token,
+                                    self.image_decoder_position_embedding, self.image_decoder, self.image_decoder_norm,
+                                    self.image_decoder_pred, g, self.NUM_OBS_TOKEN_PER_IMAGE, self.NUM_MASK_TOKEN, D)
+            image_pred = out.view(B * S, g, self.pred_num, self.NUM_MASK_TOKEN // self.pred_num, -1)
+        if self.depth_pred and mode == "train":
+            if self.share_query:
+                feat = transformer_output[:, :, P0 + cur:P0 + cur + self.NUM_DEPTH_TOKEN, q4:2 * q4]
+                cur = 0
+            else:
+                feat = transformer_output[:, :, P0 + cur:P0 + cur + self.NUM_DEPTH_TOKEN, :]
+                cur += self.NUM_DEPTH_TOKEN
+            g = self.NUM_DEPTH_TOKEN // self.NUM_OBS_TOKEN_PER_DEPTH
+            out = _WorldDecoder.run(feat, self.depth_decoder_obs_pred_projector, self.depth_mask_token,
+                                    self.depth_decoder_position_embedding, self.depth_decoder, self.depth_decoder_norm,
+                                    self.depth_decoder_pred, g, self.NUM_OBS_TOKEN_PER_DEPTH, self.NUM_DEPTH_MASK_TOKEN, D,
+                                    act="relu")                                             # F.relu (:842) fused
+            depth_pred = out.view(B * S, g, self.pred_num, self.NUM_DEPTH_MASK_TOKEN // self.pred_num, -1)
+        if self.dino_feat_pred and mode == "train":
+            if self.share_query:
+                feat = transformer_output[:, :, P0 + cur:P0 + cur + self.NUM_DINO_TOKEN, 2 * q4:3 * q4]
+                cur = 0
+            else:
+                feat = transformer_output[:, :, P0 + cur:P0 + cur + self.NUM_DINO_TOKEN, :]
+                cur += self.NUM_DINO_TOKEN
+            g = self.NUM_DINO_TOKEN // self.NUM_OBS_TOKEN_PER_DINO
+            out = _WorldDecoder.run(feat, self.dino_decoder_obs_pred_projector, self.dino_mask_token,
+                                    self.dino_decoder_position_embedding, self.dino_feat_decoder, self.dino_decoder_norm,
+                                    self.dino_decoder_pred, g, self.NUM_OBS_TOKEN_PER_DINO, self.NUM_DINO_MASK_TOKEN, D)
+            dino_pred = out.view(B * S, g, self.pred_num, self.NUM_DINO_MASK_TOKEN // self.pred_num, -1)
+        if self.sam_feat_pred and mode == "train":
+            if self.share_query:
+                feat = transformer_output[:, :, P0 + cur:P0 + cur + self.NUM_SAM_TOKEN, 3 * q4:D]
+                cur = 0
+            else:
+                feat = transformer_output[:, :, P0 + cur:P0 + cur + self.NUM_SAM_TOKEN, :]
+                cur += self.NUM_SAM_TOKEN
+            g = self.NUM_SAM_TOKEN // self.NUM_OBS_TOKEN_PER_SAM
+            out = _WorldDecoder.run(feat, self.sam_decoder_obs_pred_projector, self.sam_mask_token,
+                                    self.sam_decoder_position_embedding, self.sam_feat_decoder, self.sam_decoder_norm,
+                                    self.sam_decoder_pred, g, self.NUM_OBS_TOKEN_PER_SAM, self.NUM_SAM_MASK_TOKEN, D)
+            sam_pred = out.view(B * S, g, self.pred_num, self.NUM_SAM_MASK_TOKEN // self.pred_num, -1)
+        if self.trajectory_pred and mode == "train":
+            feat = transformer_output[:, :, P0 + cur:P0 + cur + self.NUM_TRAJ_TOKEN, :]
+            g = self.NUM_TRAJ_TOKEN // self.NUM_OBS_TOKEN_PER_TRAJ
+            out = _WorldDecoder.run(feat, self.traj_decoder_obs_pred_projector, self.traj_mask_token,
+                                    self.traj_decoder_position_embedding, self.traj_decoder, self.traj_decoder_norm,
+                                    self.traj_decoder_pred, g, self.NUM_OBS_TOKEN_PER_TRAJ, self.NUM_TRAJ_MASK_TOKEN, D)
+            traj_pred = out.view(B * S, g, self.pred_num, self.NUM_TRAJ_MASK_TOKEN // self.pred_num, -1)
+            cur += self.NUM_TRAJ_TOKEN
+
+        # ---- action head (:915-987) ----
+        if self.action_pred_steps > 0:
+            n_obs = self._this_num_obs_token()
+            action_pred_feature = transformer_output[:, :, P0 + n_obs:P0 + n_obs + self.action_pred_steps, :]
+            if not self.use_dit_head:
+                h = self.action_decoder[0](action_pred_feature, act="relu")
+                h = self.action_decoder[2](h, act="relu")
+                arm_pred_action = torch.tanh(self.arm_action_decoder[0](h).float()).to(dt)
+                gripper_pred_action = torch.sigmoid(self.gripper_action_decoder[0](h).float()).to(dt)
+            elif mode == "train":
+                feat = action_pred_feature[:, :self.sequence_length - self.atten_goal].flatten(0, 1)
+                labels = action_label.flatten(0, 1).to(dt)
+                rep = 8
+                arm_pred_action = self.action_model.loss(labels.repeat(rep, 1, 1), feat.repeat(rep, 1, 1),
+                                                         noise=diffusion_noise, timestep=diffusion_timestep,
+                                                         force_drop_ids=diffusion_drop_ids)
+                gripper_pred_action = arm_pred_action
+            else:  # mode == 'test': 10-step DDIM with classifier-free guidance 1.5 (:935-987)
+                bs = B * S
+                feat = action_pred_feature.flatten(0, 1)
+                cfg_scale = 1.5
+                if sample_noise is None:
+                    sample_noise = torch.randn(bs, self.action_pred_steps, self.action_model.in_channels, device=dev)
+                noise = sample_noise.to(feat.dtype)
+                noise = torch.cat([noise, noise], 0)
+                uncondition = self.action_model.net.z_embedder.uncondition.unsqueeze(0).expand(bs, self.action_pred_steps, -1)
+                z = torch.cat([feat, uncondition], 0)
+                if self.action_model.ddim_diffusion is None:
+                    self.action_model.create_ddim(ddim_step=10)
+                samples = self.action_model.ddim_diffusion.ddim_sample_loop(
+                    self.action_model.net.forward_with_cfg, noise.shape, noise, clip_denoised=False,
+                    model_kwargs=dict(z=z, cfg_scale=cfg_scale), device=dev, eta=0.0)
+                samples, _ = samples.chunk(2, dim=0)
+                arm_pred_action, gripper_pred_action = samples.unsqueeze(0)[..., :6], samples.unsqueeze(0)[..., 6:]
+        return (arm_pred_action, gripper_pred_action, image_pred, arm_pred_state, gripper_pred_state, loss_arm_action,
+                depth_pred, traj_pred, dino_pred, sam_pred)

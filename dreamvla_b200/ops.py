@@ -1,0 +1,340 @@
+"""torch.autograd.Function ops backed by libdvla_sm100.so -- the host-side mirror of the reference's PyTorch call sites.
+
+Every op here runs ONLY on the hand-written CUDA kernels (via dreamvla_b200._lib); there is no eager fallback.
+
+Gradient plumbing ("fused wgrad accumulation"): if a parameter carries `_dvla_grad` (a bf16 view into the flat
+gradient buffer owned by dreamvla_b200.utils.train_utils.FlatParams) the weight gradient GEMM accumulates straight
+into it in its epilogue and autograd receives None; 1-D parameters (biases, LayerNorm affine) accumulate in fp32 into
+`_dvla_grad32`.  Without those attributes the ops return ordinary gradient tensors (unit tests, stock optimisers).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+ACT_IDS = L.ACT_IDS
+
+# ----------------------------------------------------------------------------------------------------------------------
+# dropout seeds: one 64-bit counter per process, advanced per op call (fwd stores the seed for the bwd)
+# ----------------------------------------------------------------------------------------------------------------------
+_seed_state = {"base": 0x243F6A8885A308D3, "ctr": 0}
+
+
+def manual_seed(seed: int) -> None:
+    _seed_state["base"] = (int(seed) * 0x9E3779B97F4A7C15 + 0x632BE59BD9B4E019) & 0xFFFFFFFFFFFFFFFF
+    _seed_state["ctr"] = 0
+
+
+def next_seed() -> int:
+    _seed_state["ctr"] += 1
+    return (_seed_state["base"] + _seed_state["ctr"] * 0xD1342543DE82EF95) & 0xFFFFFFFFFFFFFFFF
+
+
+def _as2d(x):
+    return x.reshape(-1, x.shape[-1])
+
+
+def _bf16c(x):
+    x = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+    return x if x.is_contiguous() else x.contiguous()
+
+
+def _accum_grad_2d(param, a, b, a_mn, b_mn):
+    """dW = A @ B^T into param._dvla_grad (accumulate) or a fresh tensor."""
+    gbuf = getattr(param, "_dvla_grad", None)
+    if gbuf is not None:
+        g2 = gbuf.view(param.shape)
+        L.gemm(a, b, a_mn=a_mn, b_mn=b_mn, out=g2, residual=g2)
+        return None
+    return L.gemm(a, b, a_mn=a_mn, b_mn=b_mn)
+
+
+def _accum_bias_grad(param, dy2d):
+    g32 = getattr(param, "_dvla_grad32", None)
+    if g32 is not None:
+        L.colsum_accum(dy2d, g32)
+        return None
+    tmp = torch.zeros(dy2d.shape[1], device=dy2d.device, dtype=torch.float32)
+    L.colsum_accum(dy2d, tmp)
+    return tmp.to(torch.bfloat16)
+
+
+class _Linear(torch.autograd.Function):
+    """y = dropout(act(x @ W^T + b)) + residual.   weight_kn=False: W is [out,in] (nn.Linear); True: [in,out] (HF Conv1D)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, act, weight_kn, dropout_p, alpha):
+        x2 = _as2d(_bf16c(x))
+        N = weight.shape[1] if weight_kn else weight.shape[0]
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or
+                                                 (bias is not None and bias.requires_grad) or
+                                                 (residual is not None and residual.requires_grad))
+        aux = None
+        if act != 0 and need_grad:
+            aux = torch.empty((x2.shape[0], N), device=x2.device, dtype=torch.bfloat16)
+        seed = next_seed() if dropout_p > 0 else 0
+        res2 = _as2d(_bf16c(residual)) if residual is not None else None
+        y = L.gemm(x2, weight, b_mn=weight_kn, bias=bias, act=act, residual=res2, aux_out=aux, alpha=alpha,
+                   dropout_p=dropout_p, dropout_seed=seed)
+        ctx.save_for_backward(x2, aux)
+        ctx.weight, ctx.bias = weight, bias
+        ctx.meta = (act, weight_kn, dropout_p, seed, alpha, x.shape, residual is not None,
+                    residual.shape if residual is not None else None)
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, aux = ctx.saved_tensors
+        weight, bias = ctx.weight, ctx.bias
+        act, weight_kn, dropout_p, seed, alpha, xshape, has_res, res_shape = ctx.meta
+        dy2 = _as2d(_bf16c(dy))
+        d_res = dy.view(res_shape) if has_res and ctx.needs_input_grad[3] else None
+        dz = dy2  # gradient w.r.t. (act output before dropout)
+        if dropout_p > 0:
+            dz = L.dropout(dy2, dropout_p, seed)
+        if act != 0:
+            dz = L.act_bwd(dz, aux, act)      # gradient w.r.t. the pre-activation (alpha*acc + bias)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            # dX[M,K] = dZ[M,N] @ W ; contraction over N.  W [N,K] -> B(n_out=k, k_contr=n) = W[n, k]: MN-major B.
+            dx = L.gemm(dz, weight, b_mn=not weight_kn, alpha=alpha).view(xshape)
+        if weight.requires_grad:
+            if weight_kn:   # dW[K,N] = X^T dZ : A = X as [K x M] (mn-major), B = dZ as [N x M] (mn-major)
+                dw = _accum_grad_2d(weight, x2, dz, True, True) if alpha == 1.0 else None
+            else:           # dW[N,K] = dZ^T X
+                dw = _accum_grad_2d(weight, dz, x2, True, True) if alpha == 1.0 else None
+            if alpha != 1.0:
+                raise RuntimeError("alpha != 1 with trainable weight is not supported")
+        if bias is not None and bias.requires_grad:
+            db = _accum_bias_grad(bias, dz)
+        return dx, dw, db, d_res, None, None, None, None
+
+
+def linear(x, weight, bias=None, *, act=None, residual=None, weight_kn=False, dropout_p=0.0, alpha=1.0):
+    """Fused linear layer on the tcgen05 GEMM.  x [..., K] bf16."""
+    return _Linear.apply(x, weight, bias, residual, ACT_IDS[act] if not isinstance(act, int) else act, weight_kn,
+                         float(dropout_p), float(alpha))
+
+
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        x2 = _as2d(_bf16c(x))
+        need = torch.is_grad_enabled() and (x.requires_grad or (gamma is not None and gamma.requires_grad))
+        y, mean, rstd = L.layernorm_fwd(x2, gamma, beta, eps, save_stats=need)
+        if need:
+            ctx.save_for_backward(x2, mean, rstd)
+        ctx.gamma, ctx.beta = gamma, beta
+        ctx.xshape = x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, mean, rstd = ctx.saved_tensors
+        gamma, beta = ctx.gamma, ctx.beta
+        dy2 = _as2d(_bf16c(dy))
+        dg = db = None
+        dg32 = db32 = None
+        fused = False
+        if gamma is not None and gamma.requires_grad:
+            dg32 = getattr(gamma, "_dvla_grad32", None)
+            db32 = getattr(beta, "_dvla_grad32", None) if beta is not None else None
+            fused = dg32 is not None
+            if not fused:
+                dg32 = torch.zeros(x2.shape[1], device=x2.device, dtype=torch.float32)
+                db32 = torch.zeros(x2.shape[1], device=x2.device, dtype=torch.float32) if beta is not None else None
+        dx = L.layernorm_bwd(dy2, x2, gamma, mean, rstd, dg32, db32)
+        if dg32 is not None and not fused:
+            dg = dg32.to(torch.bfloat16)
+            db = db32.to(torch.bfloat16) if db32 is not None else None
+        return dx.view(ctx.xshape), dg, db, None
+
+
+def layer_norm(x, gamma, beta, eps=1e-5):
+    return _LayerNorm.apply(x, gamma, beta, float(eps))
+
+
+class AttnMask:
+    """Bit-matrix visibility mask + per-tile flags, built once per mask (dreamvla_model.py:25-66 semantics:
+    additive 0 -> visible, -inf -> hidden).  Shared across batch and heads."""
+
+    def __init__(self, visible_bool: torch.Tensor, device):
+        assert visible_bool.dim() == 2 and visible_bool.dtype == torch.bool
+        Lq, Lk = visible_bool.shape
+        words = (Lk + 31) // 32
+        padded = torch.zeros(Lq, words * 32, dtype=torch.bool)
+        padded[:, :Lk] = visible_bool.cpu()
+        w = padded.view(Lq, words, 32).to(torch.int64)
+        bits = (w << torch.arange(32, dtype=torch.int64)).sum(-1)
+        bits = torch.where(bits >= 2 ** 31, bits - 2 ** 32, bits).to(torch.int32)
+        self.Lq, self.Lk = Lq, Lk
+        self.bits = bits.to(device).contiguous()
+        self.flags = L.attn_mask_tiles(self.bits, Lq, Lk)
+
+    @staticmethod
+    def from_additive(mask_float: torch.Tensor, device):
+        return AttnMask(mask_float == 0, device)
+
+    @staticmethod
+    def causal(n: int, device):
+        return AttnMask(torch.ones(n, n, dtype=torch.bool).tril(), device)
+
+
+class _Attention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, scale, mask, dropout_p):
+        need = torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad)
+        seed = next_seed() if dropout_p > 0 else 0
+        bits = mask.bits if mask is not None else None
+        flags = mask.flags if mask is not None else None
+        if mask is not None:
+            assert mask.Lq == q.shape[1] and mask.Lk == k.shape[1], "mask shape mismatch"
+        o, lse = L.attn_fwd(q, k, v, scale, bits, flags, dropout_p, seed, need_lse=need)
+        if need:
+            ctx.save_for_backward(q, k, v, o, lse)
+        ctx.meta = (scale, mask, dropout_p, seed)
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        q, k, v, o, lse = ctx.saved_tensors
+        scale, mask, dropout_p, seed = ctx.meta
+        d_o = _bf16c(d_o)
+        # if q, k, v are slices of one fused [B, L, 3, H, 64] buffer, produce the gradient in the same fused layout
+        fused = (q.dim() == 4 and q._base is not None and q._base is k._base and q._base is v._base and
+                 q._base.dim() == 5 and q._base.shape[2] == 3 and q._base.is_contiguous())
+        if fused:
+            dqkv = torch.empty_like(q._base)
+            dq, dk, dv = dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2]
+        else:
+            dq = torch.empty(q.shape, device=q.device, dtype=torch.bfloat16)
+            dk = torch.empty(k.shape, device=k.device, dtype=torch.bfloat16)
+            dv = torch.empty(v.shape, device=v.device, dtype=torch.bfloat16)
+        L.attn_bwd(q, k, v, o, d_o, lse, scale, dq, dk, dv, mask.bits if mask is not None else None,
+                   mask.flags if mask is not None else None, dropout_p, seed)
+        return dq, dk, dv, None, None, None
+
+
+def attention(q, k, v, scale, mask: AttnMask | None = None, dropout_p: float = 0.0):
+    """q [B,Lq,H,64], k/v [B,Lk,H,64] (strided views allowed) -> [B,Lq,H,64] contiguous."""
+    return _Attention.apply(q, k, v, float(scale), mask, float(dropout_p))
+
+
+class _FusedQKVAttention(torch.autograd.Function):
+    """Self-attention on a fused qkv buffer [B, L, 3, H, 64]; the backward writes one fused dqkv buffer (no cat)."""
+
+    @staticmethod
+    def forward(ctx, qkv, scale, mask, dropout_p):
+        need = torch.is_grad_enabled() and qkv.requires_grad
+        seed = next_seed() if dropout_p > 0 else 0
+        q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+        o, lse = L.attn_fwd(q, k, v, scale, mask.bits if mask is not None else None,
+                            mask.flags if mask is not None else None, dropout_p, seed, need_lse=need)
+        if need:
+            ctx.save_for_backward(qkv, o, lse)
+        ctx.meta = (scale, mask, dropout_p, seed)
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        qkv, o, lse = ctx.saved_tensors
+        scale, mask, dropout_p, seed = ctx.meta
+        d_o = _bf16c(d_o)
+        dqkv = torch.empty_like(qkv)
+        L.attn_bwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], o, d_o, lse, scale, dqkv[:, :, 0], dqkv[:, :, 1],
+                   dqkv[:, :, 2], mask.bits if mask is not None else None, mask.flags if mask is not None else None,
+                   dropout_p, seed)
+        return dqkv, None, None, None
+
+
+def self_attention_fused(qkv, scale, mask: AttnMask | None = None, dropout_p: float = 0.0):
+    """qkv [B, L, 3, H, 64] contiguous bf16 -> [B, L, H, 64]."""
+    assert qkv.dim() == 5 and qkv.shape[2] == 3 and qkv.shape[4] == 64 and qkv.is_contiguous()
+    return _FusedQKVAttention.apply(qkv, float(scale), mask, float(dropout_p))
+
+
+class _Dropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p):
+        seed = next_seed()
+        ctx.meta = (p, seed, x.shape)
+        return L.dropout(_as2d(_bf16c(x)), p, seed).view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        p, seed, shape = ctx.meta
+        return L.dropout(_as2d(_bf16c(dy)), p, seed).view(shape), None
+
+
+def dropout(x, p: float, training: bool = True):
+    if not training or p <= 0:
+        return x
+    return _Dropout.apply(x, float(p))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# fused losses: value is accumulated into a caller-provided fp32 scalar; gradient produced in the same pass
+# ----------------------------------------------------------------------------------------------------------------------
+class _LossBase(torch.autograd.Function):
+    @staticmethod
+    def backward(ctx, dloss):
+        (dpred,) = ctx.saved_tensors
+        # dpred already carries the loss weight; dloss is the upstream scalar (1/accum etc.)
+        if ctx.unit_upstream:
+            return (dpred.view(ctx.pshape),) + (None,) * ctx.nrest
+        return ((dpred.float() * dloss).to(torch.bfloat16).view(ctx.pshape),) + (None,) * ctx.nrest
+
+
+class _MSELoss(_LossBase):
+    @staticmethod
+    def forward(ctx, pred, label, row_mask, weight, unit_upstream):
+        p2, l2 = _as2d(_bf16c(pred)), _as2d(_bf16c(label))
+        loss = torch.zeros(1, device=pred.device, dtype=torch.float32)
+        dpred = torch.empty_like(p2) if pred.requires_grad else None
+        L.mse_loss(p2, l2, row_mask, weight, loss, dpred)
+        if dpred is not None:
+            ctx.save_for_backward(dpred)
+        ctx.pshape, ctx.nrest, ctx.unit_upstream = pred.shape, 4, unit_upstream
+        return loss[0]
+
+
+def mse_loss(pred, label, row_mask=None, weight=1.0, unit_upstream=False):
+    """weight * mean((pred*m - label*m)^2); row_mask fp32 [rows] of {0,1} (train_utils.py:325-337)."""
+    return _MSELoss.apply(pred, label, row_mask, float(weight), unit_upstream)
+
+
+class _CosineLoss(_LossBase):
+    @staticmethod
+    def forward(ctx, pred, label, weight, unit_upstream):
+        p2, l2 = _as2d(_bf16c(pred)), _as2d(_bf16c(label))
+        loss = torch.zeros(1, device=pred.device, dtype=torch.float32)
+        dpred = torch.empty_like(p2) if pred.requires_grad else None
+        L.cosine_loss(p2, l2, weight, loss, dpred)
+        if dpred is not None:
+            ctx.save_for_backward(dpred)
+        ctx.pshape, ctx.nrest, ctx.unit_upstream = pred.shape, 3, unit_upstream
+        return loss[0]
+
+
+def cosine_loss(pred, label, weight=1.0, unit_upstream=False):
+    """weight * mean(1 - cos(pred, label, dim=-1))  (train_utils.py:423-425)."""
+    return _CosineLoss.apply(pred, label, float(weight), unit_upstream)
+
+
+class _SiLogLoss(_LossBase):
+    @staticmethod
+    def forward(ctx, pred, label, lambd, weight, unit_upstream):
+        p, l = _bf16c(pred), _bf16c(label)
+        loss = torch.zeros(1, device=pred.device, dtype=torch.float32)
+        dpred = torch.empty_like(p) if pred.requires_grad else None
+        L.silog_loss(p, l, lambd, weight, loss, dpred)
+        if dpred is not None:
+            ctx.save_for_backward(dpred)
+        ctx.pshape, ctx.nrest, ctx.unit_upstream = pred.shape, 4, unit_upstream
+        return loss[0]
+
+
+def silog_loss(pred, label, lambd=0.5, weight=1.0, unit_upstream=False):
+    """Scale-invariant log loss (utils/sigloss.py:11-15); pred, label same shape (any)."""
+    return _SiLogLoss.apply(pred, label, float(lambd), float(weight), unit_upstream)

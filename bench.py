@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- train-step samples/sec of the DreamVLA hot path (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B_per_gpu] [--config calvin|libero]
+
+Workload (config.workload): BASELINE.json configs[1] -- CALVIN ABC-D train step, bf16, sequence_length 10, all five
+world-knowledge heads (RGB / depth / DINO / SAM / flow) + DiT action head, L = 1290 backbone tokens, per-GPU batch 2
+(scripts/CALVIN_ABC_D/DreamVLA/finetune.sh:21), GPT-2 dropouts 0.1 as in the reference's training mode.
+A step = forward + 7 losses + backward + gradient all-reduce (N > 1) + global-norm clip + AdamW.
+`value` times steps on device-resident synthetic inputs (CUDA events, barrier + synchronize both sides, max over ranks);
+`e2e` times the same public API call with pinned-host inputs copied H2D and the loss copied D2H inside the timed region.
+`--impl reference` times the reference's own algorithm on the host CPU cores (oracle port of the reference modules,
+pinned against the unmodified reference by tests/test_oracle_cpu.py) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=2, help="per-GPU batch (finetune.sh uses 2)")
+    ap.add_argument("--config", default="calvin", choices=["calvin", "libero"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dropout", type=float, default=0.1)
+    ap.add_argument("--layers", type=int, default=24, help=argparse.SUPPRESS)  # debugging only; bench lines use 24
+    return ap.parse_args()
+
+
+CONFIGS = {
+    # scripts/CALVIN_ABC_D/DreamVLA/finetune.sh + --dino_feat_pred/--trajectory_pred
+    "calvin": dict(model=dict(sequence_length=10, num_resampler_query=16, num_obs_token_per_image=9, obs_pred=True,
+                              depth_pred=True, trajectory_pred=True, dino_feat_pred=True, sam_feat_pred=True,
+                              action_pred_steps=3, transformer_layers=24, hidden_dim=1024, transformer_heads=16,
+                              phase="finetune", track_label_patch_size=8, use_dit_head=True, attn_implementation="sdpa"),
+                   step=dict(sequence_length=10, future_steps=3, action_pred_steps=3, use_dit_head=True, loss_action=True,
+                             loss_image=True, loss_depth=True, loss_dino_feat=True, loss_sam_feat=True, loss_trajectory=True,
+                             flow_as_mask=True, learning_rate=1e-3, weight_decay=1e-4),
+                   heads=dict(depth=True, dino=True, sam=True, traj=True),
+                   tf_per_sample=7.202, name="CALVIN ABC-D train step, bf16, S=10, L=1290, heads RGB+depth+DINO+SAM+flow, DiT-B"),
+    # scripts/LIBERO/DreamVLA/finetune_long.sh minus world heads
+    "libero": dict(model=dict(sequence_length=7, num_resampler_query=16, num_obs_token_per_image=9, obs_pred=False,
+                              depth_pred=False, trajectory_pred=False, dino_feat_pred=False, sam_feat_pred=False,
+                              action_pred_steps=3, transformer_layers=24, hidden_dim=1024, transformer_heads=16,
+                              phase="finetune", use_dit_head=True, attn_implementation="sdpa", gripper_width=True),
+                   step=dict(sequence_length=7, future_steps=3, action_pred_steps=3, use_dit_head=True, loss_action=True,
+                             learning_rate=1e-3, weight_decay=1e-4, gripper_width=True),
+                   heads=dict(),
+                   tf_per_sample=1.280, name="LIBERO train step, bf16, S=7, L=273, world heads off, DiT-B"),
+}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        super().__init__(daemon=True)
+        self.gpu_index = gpu_index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.gpu_index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm, reasons, mx = [], set(), None
+        for s in self.samples:
+            try:
+                sm.append(float(s[1]))
+                mx = float(s[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:  # noqa: BLE001
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1442.1), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 1400.0, "fallback (B200_PROFILING.md sustained)"
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def build_model(cfg, device, dropout, layers=None):
+    from dreamvla_b200.models import DreamVLA
+    mk = dict(cfg["model"])
+    if layers is not None:
+        mk["transformer_layers"] = layers
+    torch.manual_seed(0)
+    model = DreamVLA(finetune_type="calvin", clip_device="cpu", vit_checkpoint_path=None, **mk)
+    model = model.bfloat16().to(device)
+    model.clip_model.requires_grad_(False)
+    model._init_model_type()
+    model.train()
+    gp = model.transformer_backbone
+    gp.embd_pdrop = dropout
+    for blk in gp.h:
+        blk.attn.attn_pdrop = blk.attn.resid_pdrop = blk.mlp.resid_pdrop = dropout
+    return model
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from dreamvla_b200 import _lib
+    from dreamvla_b200.utils.train_utils import StepConfig, TrainStep, synthetic_batch
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = CONFIGS[args.config]
+    scfg = StepConfig(**cfg["step"])
+    model = build_model(cfg, dev, args.dropout, args.layers)
+    step = TrainStep(model, scfg, world_size=world)
+    if world > 1:   # DDP ctor semantics: rank 0's parameters everywhere
+        dist.broadcast(step.flat.P, src=0)
+    heads = dict(cfg["heads"], flow_mask=scfg.flow_as_mask)
+    B = args.batch
+    batch = synthetic_batch(scfg, B, dev, seed=1234 + rank, heads=heads)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident timing ----
+    for _ in range(max(args.warmup, 3)):
+        loss = step(batch)
+    sync_all()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(batch)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - n0
+    if sampler:
+        sampler.stop_flag.set()
+        sampler.join()
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    ms_per_step = ms / args.steps
+    value = B * world / (ms_per_step / 1e3)
+    final_loss = float(loss)
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM): per-launch CUDA events over one instrumented step ----
+    roof = None
+    if rank == 0:
+        recs = []
+        orig = _lib.gemm
+
+        def timed_gemm(a, b, **kw):
+            a_mn, b_mn = kw.get("a_mn", False), kw.get("b_mn", False)
+            M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+            N = b.shape[1] if b_mn else b.shape[0]
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            out = orig(a, b, **kw)
+            s1.record()
+            recs.append((2.0 * M * N * K, s0, s1, min(a.stride(0), b.stride(0)) % 8 == 0))
+            return out
+        _lib.gemm = timed_gemm
+        try:
+            step.forward_backward(batch)
+        finally:
+            _lib.gemm = orig
+        torch.cuda.synchronize()
+        step.flat.G.zero_()
+        fl = sum(r[0] for r in recs if r[3])
+        tm = sum(r[1].elapsed_time(r[2]) for r in recs if r[3])
+        peak, how = measured_peaks()
+        ach = fl / (tm * 1e-3) / 1e12 if tm > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all tcgen05 GEMM launches of one fwd+bwd)",
+                "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4),
+                "peak_source": how, "traffic": None, "launches": len(recs), "gemm_ms_per_step": round(tm, 3),
+                "gemm_share_of_step": round(tm / ms_per_step, 3),
+                "step_model_tflops": round(cfg["tf_per_sample"] * B / (ms_per_step * 1e-3), 1),
+                "step_frac_of_peak": round(cfg["tf_per_sample"] * B / (ms_per_step * 1e-3) / peak, 4)}
+
+    # ---- end-to-end: pinned host inputs -> H2D -> step -> D2H loss, every step ----
+    e2e = None
+    if not args.no_e2e:
+        host = synthetic_batch(scfg, B, dev, seed=1234 + rank, heads=heads, pin=True)
+        dbuf = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+        loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+        def e2e_step():
+            for k, v in host.items():
+                dbuf[k].copy_(v, non_blocking=True)
+            ls = step(dbuf)
+            loss_host.copy_(ls.reshape(1).float(), non_blocking=True)
+        for _ in range(3):
+            e2e_step()
+        sync_all()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        e1.record()
+        sync_all()
+        wall = (time.perf_counter() - t0) * 1e3
+        t = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t) / args.steps
+        e2e = {"value": round(B * world / (e2e_ms / 1e3), 3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms, 3), "wall_ms_per_step": round(wall / args.steps, 3)}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        cpu = cpu_baseline(args, steps=1, warm=0)
+
+    if rank == 0:
+        line = {
+            "metric": "train_step_samples_per_sec", "value": round(value, 3), "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": cfg["name"], "per_gpu_batch": B, "global_batch": B * world,
+                       "seq_len": cfg["model"]["sequence_length"], "parallelism": f"dp{world}",
+                       "dropout": args.dropout, "layers": args.layers,
+                       "l2": "inputs+weights+activations per step >> 126 MB L2 (1.3 GB of bf16 weights re-read every step); no explicit flush",
+                       "trainable_params": step.flat.num_params, "final_loss": final_loss},
+            "clocks": sampler.summary() if sampler else None,
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_baseline(args, steps=1, warm=0, budget_s=150.0):
+    """The reference's algorithm (oracle port, fp32) on the host cores: fwd + losses + bwd + clip + AdamW, B = 1 window."""
+    from oracle import dreamvla_oracle as O
+    from tests import synth
+    from tests.state_template import build_template
+    cfg = CONFIGS[args.config]
+    mk = dict(cfg["model"], batch=1, weight_seed=1, input_seed=2)
+    if args.layers is not None:
+        mk["transformer_layers"] = args.layers
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth.synth_state_dict(build_template(mk), 1)
+    frozen = ("vision_encoder.", "clip_model.", "attention_mask", "position_embedding")
+    params = []
+    for k, v in sd.items():
+        if v.is_floating_point() and not any(f in k for f in frozen):
+            v.requires_grad_(True)
+            params.append(v)
+    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=1e-4)
+    inp = synth.synth_inputs(mk)
+    S = mk["sequence_length"]
+    lab = synth.synth_labels(mk)
+    g = torch.Generator().manual_seed(3)
+    noise = torch.randn(8 * S, 3, 7, generator=g)
+    tstep = torch.randint(0, 100, (8 * S,), generator=g)
+    drop = torch.rand(8 * S, generator=g) < 0.1
+    lcfg = dict(mk, future_steps=3, flow_as_mask=cfg["step"].get("flow_as_mask", False))
+
+    def one():
+        opt.zero_grad(set_to_none=True)
+        with torch.no_grad():   # the reference runs ViT and CLIP under no_grad (dreamvla_model.py:643,670)
+            pass
+        fwd = O.dreamvla_forward(sd, mk, inp["image_primary"], inp["image_wrist"], inp["state"], inp["text_token"],
+                                 action_label=inp["action_label"], diffusion_noise=noise, diffusion_timestep=tstep,
+                                 diffusion_drop_ids=drop)
+        losses = O.train_losses(lcfg, fwd, lab)
+        losses["loss"].backward()
+        torch.nn.utils.clip_grad_norm_(params, 0.1)
+        opt.step()
+        return float(losses["loss"])
+    times = []
+    t_all = time.perf_counter()
+    for i in range(warm + steps):
+        t0 = time.perf_counter()
+        one()
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
+        if time.perf_counter() - t_all > budget_s and len(times) >= 1:
+            break
+    sec = sum(times) / len(times)
+    return {"value": round(1.0 / sec, 5), "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"{len(times)} train step(s) (fwd+7 losses+bwd+clip+AdamW, fp32) of ONE sample window (B=1) of the same "
+                      f"workload; {sec:.1f} s/step", "steps_timed": len(times), "s_per_step": round(sec, 2)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = CONFIGS[args.config]
+    cb = cpu_baseline(args, steps=args.steps, warm=min(args.warmup, 1), budget_s=180.0)
+    line = {"impl": "reference", "metric": "train_step_samples_per_sec", "value": cb["value"], "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": cb["steps_timed"], "warmup": min(args.warmup, 1),
+            "ms_per_step": round(cb["s_per_step"] * 1e3, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["name"], "per_gpu_batch": 1, "global_batch": 1,
+                       "seq_len": cfg["model"]["sequence_length"], "parallelism": "cpu"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -24,7 +24,7 @@ class GemmArgs(C.Structure):
     _fields_ = [("a", _vp), ("b", _vp), ("out", _vp), ("bias", _vp), ("residual", _vp), ("aux_out", _vp),
                 ("aux_in", _vp), ("M", _i64), ("N", _i64), ("K", _i64), ("lda", _i64), ("ldb", _i64), ("ldo", _i64),
                 ("ldr", _i64), ("ld_aux", _i64), ("a_mn_major", _i32), ("b_mn_major", _i32), ("act", _i32),
-                ("out_fp32", _i32), ("alpha", _f32), ("dropout_p", _f32), ("dropout_seed", _u64)]
+                ("out_fp32", _i32), ("alpha", _f32), ("dropout_p", _f32), ("dropout_seed", _u64), ("dropout_seed_ptr", _vp)]
 
 
 class LayerNormFwdArgs(C.Structure):
@@ -42,7 +42,7 @@ class AttnFwdArgs(C.Structure):
                 ("B", _i64), ("H", _i64), ("Lq", _i64), ("Lk", _i64),
                 ("q_sb", _i64), ("q_ss", _i64), ("q_sh", _i64), ("k_sb", _i64), ("k_ss", _i64), ("k_sh", _i64),
                 ("v_sb", _i64), ("v_ss", _i64), ("v_sh", _i64), ("o_sb", _i64), ("o_ss", _i64), ("o_sh", _i64),
-                ("mask_words", _i32), ("scale", _f32), ("dropout_p", _f32), ("dropout_seed", _u64)]
+                ("mask_words", _i32), ("scale", _f32), ("dropout_p", _f32), ("dropout_seed", _u64), ("dropout_seed_ptr", _vp)]
 
 
 class AttnBwdArgs(C.Structure):
@@ -54,7 +54,7 @@ class AttnBwdArgs(C.Structure):
                 ("do_sb", _i64), ("do_ss", _i64), ("do_sh", _i64),
                 ("dq_sb", _i64), ("dq_ss", _i64), ("dq_sh", _i64), ("dk_sb", _i64), ("dk_ss", _i64), ("dk_sh", _i64),
                 ("dv_sb", _i64), ("dv_ss", _i64), ("dv_sh", _i64),
-                ("mask_words", _i32), ("scale", _f32), ("dropout_p", _f32), ("dropout_seed", _u64)]
+                ("mask_words", _i32), ("scale", _f32), ("dropout_p", _f32), ("dropout_seed", _u64), ("dropout_seed_ptr", _vp)]
 
 
 class AdamWArgs(C.Structure):
@@ -119,7 +119,7 @@ def _need_cuda(*ts) -> None:
 # raw op wrappers (no autograd)
 # ----------------------------------------------------------------------------------------------------------------------
 def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, act=0, residual=None, aux_out=None, aux_in=None, out=None,
-         out_dtype=torch.bfloat16, alpha=1.0, dropout_p=0.0, dropout_seed=0):
+         out_dtype=torch.bfloat16, alpha=1.0, dropout_p=0.0, dropout_seed=0, dropout_seed_ptr=None):
     """out[M,N] = epi(alpha * A @ B^T).  a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N] if b_mn); 2-D, unit inner stride."""
     _need_cuda(a, b)
     assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1, (a.shape, a.stride(), b.shape, b.stride())
@@ -150,6 +150,7 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, act=0, residual=None, aux_o
     args.alpha = float(alpha)
     args.dropout_p = float(dropout_p)
     args.dropout_seed = int(dropout_seed)
+    args.dropout_seed_ptr = _ptr(dropout_seed_ptr)
     _check(load().dvla_gemm(C.byref(args), _stream()), "dvla_gemm")
     return out
 
@@ -183,7 +184,8 @@ def _bsh(t):
     return t.stride(0), t.stride(1), t.stride(2)
 
 
-def attn_fwd(q, k, v, scale, mask_bits=None, tile_flags=None, dropout_p=0.0, dropout_seed=0, need_lse=True):
+def attn_fwd(q, k, v, scale, mask_bits=None, tile_flags=None, dropout_p=0.0, dropout_seed=0, need_lse=True,
+             dropout_seed_ptr=None):
     """q [B,Lq,H,64], k/v [B,Lk,H,64] (arbitrary batch/seq/head strides) -> o [B,Lq,H,64] contiguous, lse [B,H,Lq]."""
     _need_cuda(q, k, v)
     B, Lq, H, _ = q.shape
@@ -200,11 +202,13 @@ def attn_fwd(q, k, v, scale, mask_bits=None, tile_flags=None, dropout_p=0.0, dro
     a.o_sb, a.o_ss, a.o_sh = _bsh(o)
     a.mask_words = 0 if mask_bits is None else mask_bits.shape[1]
     a.scale, a.dropout_p, a.dropout_seed = float(scale), float(dropout_p), int(dropout_seed)
+    a.dropout_seed_ptr = _ptr(dropout_seed_ptr)
     _check(load().dvla_attn_fwd(C.byref(a), _stream()), "dvla_attn_fwd")
     return o, lse
 
 
-def attn_bwd(q, k, v, o, d_o, lse, scale, dq, dk, dv, mask_bits=None, tile_flags=None, dropout_p=0.0, dropout_seed=0):
+def attn_bwd(q, k, v, o, d_o, lse, scale, dq, dk, dv, mask_bits=None, tile_flags=None, dropout_p=0.0, dropout_seed=0,
+             dropout_seed_ptr=None):
     B, Lq, H, _ = q.shape
     Lk = k.shape[1]
     delta = torch.empty((B, H, Lq), device=q.device, dtype=torch.float32)
@@ -224,6 +228,7 @@ def attn_bwd(q, k, v, o, d_o, lse, scale, dq, dk, dv, mask_bits=None, tile_flags
     a.dv_sb, a.dv_ss, a.dv_sh = _bsh(dv)
     a.mask_words = 0 if mask_bits is None else mask_bits.shape[1]
     a.scale, a.dropout_p, a.dropout_seed = float(scale), float(dropout_p), int(dropout_seed)
+    a.dropout_seed_ptr = _ptr(dropout_seed_ptr)
     _check(load().dvla_attn_bwd(C.byref(a), _stream()), "dvla_attn_bwd")
 
 
@@ -248,12 +253,13 @@ def accum_fp32_into_bf16(src_f32, dst_bf16):
                                             _i64(src_f32.numel()), _stream()), "dvla_accum_fp32_into_bf16")
 
 
-def dropout(x2d, p, seed, out=None):
+def dropout(x2d, p, seed, out=None, seed_ptr=None):
     rows, N = x2d.shape
     assert x2d.stride(1) == 1
     y = torch.empty((rows, N), device=x2d.device, dtype=torch.bfloat16) if out is None else out
     _check(load().dvla_dropout(C.c_void_p(x2d.data_ptr()), C.c_void_p(y.data_ptr()), _i64(rows), _i64(N),
-                               _i64(x2d.stride(0)), _i64(y.stride(0)), _f32(p), _u64(seed), _stream()), "dvla_dropout")
+                               _i64(x2d.stride(0)), _i64(y.stride(0)), _f32(p), _u64(seed), C.c_void_p(_ptr(seed_ptr)),
+                               _stream()), "dvla_dropout")
     return y
 
 

@@ -32,7 +32,7 @@ struct AttnParams {
   long long q_sb, q_ss, q_sh, k_sb, k_ss, k_sh, v_sb, v_ss, v_sh, o_sb, o_ss, o_sh;
   long long do_sb, do_ss, do_sh, dq_sb, dq_ss, dq_sh, dk_sb, dk_ss, dk_sh, dv_sb, dv_ss, dv_sh;
   float scale;
-  float drop_scale; uint32_t drop_thresh; uint64_t drop_seed;
+  float drop_scale; uint32_t drop_thresh; uint64_t drop_seed; const uint64_t* drop_seed_ptr;
 };
 
 // ---- smem tile helpers: 64 rows x 64 bf16 (128 B per row), 16-byte chunk c of row r stored at chunk c ^ (r & 7) --------
@@ -140,6 +140,7 @@ __device__ __forceinline__ void dropout_bits(const AttnParams& p, long long bh, 
                                              bool transposed, uint32_t (&keep)[8] /* per n-tile: 4 bits e0..e3 */) {
   const int lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
   const int nblk = (p.Lk + 7) >> 3;
+  const uint64_t seed = p.drop_seed + (p.drop_seed_ptr ? __ldg(p.drop_seed_ptr) : 0ull);
   if (!transposed) {
     // rows = queries, cols = keys: one RNG block == one n-tile of one row.
     uint32_t m[2][2];
@@ -149,7 +150,7 @@ __device__ __forceinline__ void dropout_bits(const AttnParams& p, long long bh, 
       for (int half = 0; half < 2; ++half) {
         const int t = c + half * 4;
         const long long row = frag_row0 + g + r * 8;
-        m[r][half] = dropout_keep8(p.drop_seed, (bh * p.Lq + row) * nblk + ((frag_col0 >> 3) + t), p.drop_thresh);
+        m[r][half] = dropout_keep8(seed, (bh * p.Lq + row) * nblk + ((frag_col0 >> 3) + t), p.drop_thresh);
       }
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
@@ -168,7 +169,7 @@ __device__ __forceinline__ void dropout_bits(const AttnParams& p, long long bh, 
       for (int e = 0; e < 4; ++e) {
         const int kr = frag_row0 + g + (e >> 1) * 8;
         const long long qc = frag_col0 + t * 8 + 2 * c + (e & 1);
-        const uint32_t mk = dropout_keep8(p.drop_seed, (bh * p.Lq + qc) * nblk + (kr >> 3), p.drop_thresh);
+        const uint32_t mk = dropout_keep8(seed, (bh * p.Lq + qc) * nblk + (kr >> 3), p.drop_thresh);
         bits |= ((mk >> (kr & 7)) & 1u) << e;
       }
       keep[t] = bits;
@@ -600,6 +601,7 @@ int attn_fwd_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s) {
     p.drop_thresh = (uint32_t)(a->dropout_p * 65536.0f + 0.5f);
     p.drop_scale = 1.0f / (1.0f - (float)p.drop_thresh / 65536.0f);
     p.drop_seed = a->dropout_seed;
+    p.drop_seed_ptr = a->dropout_seed_ptr;
   }
   attn_fwd_kernel<<<dim3(p.nqt, p.H, p.B), 128, 0, s>>>(p);
   DVLA_CHECK_LAUNCH("attn_fwd");
@@ -636,6 +638,7 @@ int attn_bwd_dispatch(const dvla_attn_bwd_args* a, cudaStream_t s) {
     p.drop_thresh = (uint32_t)(a->dropout_p * 65536.0f + 0.5f);
     p.drop_scale = 1.0f / (1.0f - (float)p.drop_thresh / 65536.0f);
     p.drop_seed = a->dropout_seed;
+    p.drop_seed_ptr = a->dropout_seed_ptr;
   }
   const long long rows = (long long)p.B * p.H * p.Lq;
   attn_delta_kernel<<<(unsigned)((rows * 8 + 255) / 256), 256, 0, s>>>(p);

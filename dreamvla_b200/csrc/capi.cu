@@ -39,7 +39,7 @@ int attn_mask_tiles_dispatch(const uint32_t* mask, int32_t mask_words, int64_t L
 int colsum_accum_dispatch(const void* x, int64_t rows, int64_t N, int64_t ld, float* out, cudaStream_t s);
 int accum_fp32_into_bf16_dispatch(const float* src, void* dst, int64_t n, cudaStream_t s);
 int dropout_dispatch(const void* x, void* y, int64_t rows, int64_t N, int64_t ldx, int64_t ldy, float p, uint64_t seed,
-                     cudaStream_t s);
+                     const uint64_t* seed_ptr, cudaStream_t s);
 int act_bwd_dispatch(const void* dy, const void* pre, void* dx, int64_t n, int32_t act, cudaStream_t s);
 int mse_loss_dispatch(const void* pred, const void* label, const float* row_mask, int64_t rows, int64_t C, float weight,
                       float* loss_out, void* dpred, cudaStream_t s);
@@ -78,8 +78,8 @@ int dvla_accum_fp32_into_bf16(const float* src, void* dst, int64_t n, void* stre
   return accum_fp32_into_bf16_dispatch(src, dst, n, S(stream));
 }
 int dvla_dropout(const void* x, void* y, int64_t rows, int64_t N, int64_t ldx, int64_t ldy, float p, uint64_t seed,
-                 void* stream) {
-  return dropout_dispatch(x, y, rows, N, ldx, ldy, p, seed, S(stream));
+                 const uint64_t* seed_ptr, void* stream) {
+  return dropout_dispatch(x, y, rows, N, ldx, ldy, p, seed, seed_ptr, S(stream));
 }
 int dvla_act_bwd(const void* dy, const void* pre, void* dx, int64_t n, int32_t act, void* stream) {
   return act_bwd_dispatch(dy, pre, dx, n, act, S(stream));

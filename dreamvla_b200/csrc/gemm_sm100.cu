@@ -37,6 +37,7 @@ struct GemmParams {
   float drop_scale;        // 1/(1-p_eff), 0 => dropout disabled
   uint32_t drop_thresh;    // round(p*65536)
   uint64_t drop_seed;
+  const uint64_t* drop_seed_ptr;
 };
 
 template <int BN>
@@ -106,7 +107,8 @@ __device__ __forceinline__ void epilogue8(float (&v)[8], int row, int col, const
     // element index = row*N + col; 8-element RNG blocks need col%8==0 alignment relative to row*N -> use (row*N+col)/8
     // only when N%8==0, otherwise fall back to per-row block indexing (row*ceil(N/8) + col/8).
     const uint64_t blk = static_cast<uint64_t>(row) * static_cast<uint64_t>((p.N + 7) >> 3) + (col >> 3);
-    const uint32_t keep = dropout_keep8(p.drop_seed, blk, p.drop_thresh);
+    const uint64_t seed = p.drop_seed + (p.drop_seed_ptr ? __ldg(p.drop_seed_ptr) : 0ull);
+    const uint32_t keep = dropout_keep8(seed, blk, p.drop_thresh);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * p.drop_scale : 0.f;
   }
@@ -423,6 +425,7 @@ int gemm_dispatch(const dvla_gemm_args* a, cudaStream_t stream) {
     p.drop_thresh = (uint32_t)(a->dropout_p * 65536.0f + 0.5f);
     p.drop_scale = 1.0f / (1.0f - (float)p.drop_thresh / 65536.0f);
     p.drop_seed = a->dropout_seed;
+    p.drop_seed_ptr = a->dropout_seed_ptr;
   }
   const int oal = a->out_fp32 ? 4 : 8;
   p.vec_ok = aligned16(a->out) && (a->ldo % oal == 0) &&

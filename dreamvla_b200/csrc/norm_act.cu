@@ -274,7 +274,9 @@ int accum_fp32_into_bf16_dispatch(const float* src, void* dst, int64_t n, cudaSt
 // Dropout with the GEMM-epilogue mask convention: RNG block = row*ceil(N/8) + col/8, bit col%8.
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void dropout_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long rows, int N, long long ldx,
-                               long long ldy, uint32_t thresh, float scale, uint64_t seed, int vec) {
+                               long long ldy, uint32_t thresh, float scale, uint64_t seed0,
+                               const uint64_t* __restrict__ seed_ptr, int vec) {
+  const uint64_t seed = seed0 + (seed_ptr ? __ldg(seed_ptr) : 0ull);
   const int groups = (N + 7) >> 3;
   const long long total = rows * groups;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -297,7 +299,7 @@ __global__ void dropout_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
   }
 }
 int dropout_dispatch(const void* x, void* y, int64_t rows, int64_t N, int64_t ldx, int64_t ldy, float p, uint64_t seed,
-                     cudaStream_t s) {
+                     const uint64_t* seed_ptr, cudaStream_t s) {
   if (!x || !y) { set_error("dropout: null pointer"); return DVLA_ERR_INVALID; }
   if (p < 0.f || p >= 1.f) { set_error("dropout: p out of range"); return DVLA_ERR_INVALID; }
   if (rows <= 0 || N <= 0) return DVLA_OK;
@@ -308,7 +310,7 @@ int dropout_dispatch(const void* x, void* y, int64_t rows, int64_t N, int64_t ld
   const long long total = rows * ((N + 7) / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
-  dropout_kernel<<<(unsigned)blocks, 256, 0, s>>>((const bf16*)x, (bf16*)y, rows, (int)N, ldx, ldy, thresh, scale, seed, vec);
+  dropout_kernel<<<(unsigned)blocks, 256, 0, s>>>((const bf16*)x, (bf16*)y, rows, (int)N, ldx, ldy, thresh, scale, seed, seed_ptr, vec);
   DVLA_CHECK_LAUNCH("dropout");
   return DVLA_OK;
 }

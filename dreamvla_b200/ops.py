@@ -31,6 +31,20 @@ def next_seed() -> int:
     return (_seed_state["base"] + _seed_state["ctr"] * 0xD1342543DE82EF95) & 0xFFFFFFFFFFFFFFFF
 
 
+_seed_counters = {}
+
+
+def seed_counter(device) -> torch.Tensor:
+    """Device-resident uint64 counter added to every dropout seed at kernel run time.  The train step increments it on
+    the device each step, so CUDA-graph replays (whose host-side seeds are baked in) still draw fresh masks."""
+    key = str(device)
+    t = _seed_counters.get(key)
+    if t is None:
+        t = torch.zeros(1, device=device, dtype=torch.int64)
+        _seed_counters[key] = t
+    return t
+
+
 def _as2d(x):
     return x.reshape(-1, x.shape[-1])
 
@@ -76,7 +90,8 @@ class _Linear(torch.autograd.Function):
         seed = next_seed() if dropout_p > 0 else 0
         res2 = _as2d(_bf16c(residual)) if residual is not None else None
         y = L.gemm(x2, weight, b_mn=weight_kn, bias=bias, act=act, residual=res2, aux_out=aux, alpha=alpha,
-                   dropout_p=dropout_p, dropout_seed=seed)
+                   dropout_p=dropout_p, dropout_seed=seed,
+                   dropout_seed_ptr=seed_counter(x2.device) if dropout_p > 0 else None)
         ctx.save_for_backward(x2, aux)
         ctx.weight, ctx.bias = weight, bias
         ctx.meta = (act, weight_kn, dropout_p, seed, alpha, x.shape, residual is not None,
@@ -92,7 +107,7 @@ class _Linear(torch.autograd.Function):
         d_res = dy.view(res_shape) if has_res and ctx.needs_input_grad[3] else None
         dz = dy2  # gradient w.r.t. (act output before dropout)
         if dropout_p > 0:
-            dz = L.dropout(dy2, dropout_p, seed)
+            dz = L.dropout(dy2, dropout_p, seed, seed_ptr=seed_counter(dy2.device))
         if act != 0:
             dz = L.act_bwd(dz, aux, act)      # gradient w.r.t. the pre-activation (alpha*acc + bias)
         dx = dw = db = None
@@ -190,7 +205,8 @@ class _Attention(torch.autograd.Function):
         flags = mask.flags if mask is not None else None
         if mask is not None:
             assert mask.Lq == q.shape[1] and mask.Lk == k.shape[1], "mask shape mismatch"
-        o, lse = L.attn_fwd(q, k, v, scale, bits, flags, dropout_p, seed, need_lse=need)
+        o, lse = L.attn_fwd(q, k, v, scale, bits, flags, dropout_p, seed, need_lse=need,
+                            dropout_seed_ptr=seed_counter(q.device) if dropout_p > 0 else None)
         if need:
             ctx.save_for_backward(q, k, v, o, lse)
         ctx.meta = (scale, mask, dropout_p, seed)
@@ -212,7 +228,8 @@ class _Attention(torch.autograd.Function):
             dk = torch.empty(k.shape, device=k.device, dtype=torch.bfloat16)
             dv = torch.empty(v.shape, device=v.device, dtype=torch.bfloat16)
         L.attn_bwd(q, k, v, o, d_o, lse, scale, dq, dk, dv, mask.bits if mask is not None else None,
-                   mask.flags if mask is not None else None, dropout_p, seed)
+                   mask.flags if mask is not None else None, dropout_p, seed,
+                   dropout_seed_ptr=seed_counter(q.device) if dropout_p > 0 else None)
         return dq, dk, dv, None, None, None
 
 
@@ -230,7 +247,8 @@ class _FusedQKVAttention(torch.autograd.Function):
         seed = next_seed() if dropout_p > 0 else 0
         q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
         o, lse = L.attn_fwd(q, k, v, scale, mask.bits if mask is not None else None,
-                            mask.flags if mask is not None else None, dropout_p, seed, need_lse=need)
+                            mask.flags if mask is not None else None, dropout_p, seed, need_lse=need,
+                            dropout_seed_ptr=seed_counter(qkv.device) if dropout_p > 0 else None)
         if need:
             ctx.save_for_backward(qkv, o, lse)
         ctx.meta = (scale, mask, dropout_p, seed)
@@ -244,7 +262,7 @@ class _FusedQKVAttention(torch.autograd.Function):
         dqkv = torch.empty_like(qkv)
         L.attn_bwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], o, d_o, lse, scale, dqkv[:, :, 0], dqkv[:, :, 1],
                    dqkv[:, :, 2], mask.bits if mask is not None else None, mask.flags if mask is not None else None,
-                   dropout_p, seed)
+                   dropout_p, seed, dropout_seed_ptr=seed_counter(qkv.device) if dropout_p > 0 else None)
         return dqkv, None, None, None
 
 
@@ -259,12 +277,12 @@ class _Dropout(torch.autograd.Function):
     def forward(ctx, x, p):
         seed = next_seed()
         ctx.meta = (p, seed, x.shape)
-        return L.dropout(_as2d(_bf16c(x)), p, seed).view(x.shape)
+        return L.dropout(_as2d(_bf16c(x)), p, seed, seed_ptr=seed_counter(x.device)).view(x.shape)
 
     @staticmethod
     def backward(ctx, dy):
         p, seed, shape = ctx.meta
-        return L.dropout(_as2d(_bf16c(dy)), p, seed).view(shape), None
+        return L.dropout(_as2d(_bf16c(dy)), p, seed, seed_ptr=seed_counter(dy.device)).view(shape), None
 
 
 def dropout(x, p: float, training: bool = True):

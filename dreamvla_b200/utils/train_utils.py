@@ -1,0 +1,444 @@
+"""Train step of the hot path -- B200-native mirror of reference utils/train_utils.py:59-726 (`train_one_epoch_calvin`).
+
+Reference step (train_utils.py:94-608): unpack the 13-tuple batch, build labels, forward, seven losses with weights
+(1.0 arm, 0.01 gripper, 0.1 image, 0.001 depth, 0.1 traj(x0.1), 0.01 dino, 0.01 sam, :585), `/accum`, backward (DDP
+all-reduce), clip_grad_norm_(0.1) every micro-step, AdamW / scheduler / zero_grad on accumulation boundaries.
+
+Here:
+  * FlatParams keeps parameters, gradients and AdamW moments in flat buffers; weight gradients are accumulated straight
+    into the flat gradient buffer by the wgrad GEMM epilogue (ops.py), 1-D gradients in an fp32 side buffer;
+  * losses are fused value+gradient kernels (ops.mse_loss / cosine_loss / silog_loss), no host sync in the step;
+  * data-parallel: ONE bf16 all-reduce (NCCL over NVLink) of the flat gradient buffer per micro-step on a side stream,
+    then global-norm clip + AdamW fused in two kernels (dvla_sumsq, dvla_adamw); lr / step counters live on the device.
+  * the per-step `.cpu().numpy()` visual-debug copies of the reference (:198-213, :382-396) are not part of the path.
+"""
+from __future__ import annotations
+
+import math
+import time
+from dataclasses import dataclass
+
+import torch
+import torch.nn.functional as F
+
+from .. import _lib as L
+from .. import ops
+
+# parameters that exist in the reference's module tree but never receive a gradient in forward (dreamvla_model.py:
+# 203-205 action encoders, :320-333 recon_* decoders, action_model/models.py:187 history_embedder; the frozen ViT/CLIP).
+NEVER_USED_PREFIXES = ("vision_encoder.", "clip_model.", "recon_state_decoder.", "recon_arm_state_decoder.",
+                       "recon_gripper_state_decoder.", "action_pose_encoder.", "action_gripper_position_encoder.",
+                       "action_projector.", "action_model.net.history_embedder.")
+HEAD_PREFIXES = {
+    "image": ("image_decoder", "mask_token", "obs_tokens"),
+    "depth": ("depth_decoder", "depth_mask_token", "depth_tokens"),
+    "dino": ("dino_feat_decoder", "dino_decoder", "dino_mask_token", "dino_feat_tokens"),
+    "sam": ("sam_feat_decoder", "sam_decoder", "sam_mask_token", "sam_feat_tokens"),
+    "traj": ("traj_decoder", "traj_mask_token", "trajectory_tokens"),
+}
+
+
+def get_cast_dtype(precision: str):
+    """train_utils.py:16-22."""
+    if precision in ("bf16", "amp_bf16", "amp_bfloat16"):
+        return torch.bfloat16
+    if precision == "fp16":
+        return torch.float16
+    return None
+
+
+class AverageMeter:
+    """train_utils.py:764-780."""
+
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.val = self.avg = self.sum = self.count = 0
+
+    def update(self, val, n=1):
+        self.val = val
+        self.sum += val * n
+        self.count += n
+        self.avg = self.sum / self.count
+
+
+def patchify(imgs, patch_size):
+    """train_utils.py:37-50."""
+    h = w = imgs.shape[2] // patch_size
+    x = imgs.reshape(imgs.shape[0], 3, h, patch_size, w, patch_size)
+    x = torch.einsum("nchpwq->nhwpqc", x)
+    return x.reshape(imgs.shape[0], h * w, patch_size ** 2 * 3)
+
+
+def normalize_patchfied_image(x):
+    """train_utils.py:52-57 (unbiased variance, eps 1e-6)."""
+    mean = x.mean(dim=-1, keepdim=True)
+    var = x.var(dim=-1, keepdim=True)
+    return (x - mean) / (var + 1.0e-6) ** 0.5
+
+
+def unpatchify(patches, patch_size=16, img_size=(224, 224)):
+    """train_utils.py:783-799."""
+    B, P, n, pd = patches.shape
+    g = int(n ** 0.5)
+    C = pd // (patch_size * patch_size)
+    x = patches.view(B, P, g, g, patch_size, patch_size, C).permute(0, 1, 6, 2, 4, 3, 5).contiguous()
+    return x.view(B, P, C, *img_size)
+
+
+def patchify_map(img, patch_size=16):
+    """Inverse of `unpatchify` for C = 1 maps: [n, 1, H, W] -> [n, (H/p)(W/p), p*p].  SiLog is a mean over elements, so
+    permuting the LABEL instead of un-permuting the prediction (train_utils.py:366-371) gives the identical loss."""
+    n, _, H, W = img.shape
+    g = H // patch_size
+    return img.view(n, g, patch_size, g, patch_size).permute(0, 1, 3, 2, 4).reshape(n, g * g, patch_size * patch_size)
+
+
+def flow_masks(tracks_primary, tracks_wrist):
+    """train_utils.py:274-313: 28x28 flow -> avg-pool 2x2 -> |v| > 1 -> (primary only) 3x3 max-pool dilation.
+    Returns per-patch {0,1} masks [n*196] for each camera."""
+    Bn, P, HW, C = tracks_primary.shape
+    H = W = int(HW ** 0.5)
+
+    def pool(t):
+        tp = t.reshape(Bn * P, H, W, C).permute(0, 3, 1, 2).float()
+        return (torch.norm(F.avg_pool2d(tp, kernel_size=2, stride=2), dim=1) > 1.0).unsqueeze(1).float()
+    mp = F.max_pool2d(pool(tracks_primary), kernel_size=3, stride=1, padding=1)
+    mw = pool(tracks_wrist)
+    return mp.reshape(-1).contiguous(), mw.reshape(-1).contiguous()
+
+
+@dataclass
+class StepConfig:
+    sequence_length: int = 10
+    future_steps: int = 3
+    action_pred_steps: int = 3
+    atten_goal: int = 0
+    pred_num: int = 1
+    patch_size: int = 16
+    use_dit_head: bool = True
+    loss_action: bool = True
+    loss_image: bool = False
+    loss_depth: bool = False
+    loss_dino_feat: bool = False
+    loss_sam_feat: bool = False
+    loss_trajectory: bool = False
+    flow_as_mask: bool = False
+    loss_arm_action_ratio: float = 1.0
+    loss_gripper_action_ratio: float = 0.01
+    gradient_accumulation_steps: int = 1
+    learning_rate: float = 1e-3
+    weight_decay: float = 1e-4
+    max_grad_norm: float = 0.1
+    gripper_width: bool = False
+
+    @staticmethod
+    def from_args(args):
+        kw = {f: getattr(args, f) for f in StepConfig.__dataclass_fields__ if hasattr(args, f)}
+        return StepConfig(**kw)
+
+
+class FlatParams:
+    """Flat bf16 parameter / gradient buffers + fp32 AdamW moments for the trainable, USED parameters of a DreamVLA.
+
+    Layout: [ >=2-D parameters | 1-D parameters ], each parameter 16-byte aligned.  Parameters become views of `P`;
+    `p.grad` is a view of `G`; ops accumulate weight gradients through `p._dvla_grad` and 1-D gradients in fp32
+    through `p._dvla_grad32` (folded into G by `fold_small_grads`)."""
+
+    def __init__(self, model, cfg: StepConfig, exclude_prefixes=()):
+        inactive = []
+        for head, on in (("image", cfg.loss_image), ("depth", cfg.loss_depth), ("dino", cfg.loss_dino_feat),
+                         ("sam", cfg.loss_sam_feat), ("traj", cfg.loss_trajectory)):
+            if not on:
+                inactive += list(HEAD_PREFIXES[head])
+        skip = tuple(NEVER_USED_PREFIXES) + tuple(exclude_prefixes)
+        big, small = [], []
+        self.names = []
+        for name, p in model.named_parameters():
+            if not p.requires_grad or name.startswith(skip) or any(name.startswith(pref) for pref in inactive):
+                continue
+            if not model.use_dit_head and name.startswith("action_model."):
+                continue
+            if p.dtype != torch.bfloat16 or not p.is_cuda:
+                raise RuntimeError(f"FlatParams: {name} is {p.dtype} on {p.device}; the train step is bf16/CUDA only")
+            (small if p.dim() <= 1 else big).append((name, p))
+        self.params = big + small
+        dev = self.params[0][1].device
+
+        def aligned(n):
+            return (n + 7) // 8 * 8
+        off = 0
+        offs = []
+        for _, p in self.params:
+            offs.append(off)
+            off += aligned(p.numel())
+        self.n_big = sum(aligned(p.numel()) for _, p in big)
+        self.n = off
+        self.P = torch.zeros(self.n, device=dev, dtype=torch.bfloat16)
+        self.G = torch.zeros(self.n, device=dev, dtype=torch.bfloat16)
+        self.G32 = torch.zeros(max(self.n - self.n_big, 8), device=dev, dtype=torch.float32)
+        self.m = torch.zeros(self.n, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(self.n, device=dev, dtype=torch.float32)
+        self.sumsq = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.lr = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.step_count = torch.zeros(1, device=dev, dtype=torch.float32)
+        for (name, p), o in zip(self.params, offs):
+            n = p.numel()
+            self.P[o:o + n].copy_(p.data.reshape(-1))
+            p.data = self.P[o:o + n].view(p.shape)
+            g = self.G[o:o + n].view(p.shape)
+            p.grad = g
+            p._dvla_grad = g
+            if p.dim() <= 1:
+                p._dvla_grad32 = self.G32[o - self.n_big:o - self.n_big + n]
+            self.names.append(name)
+        self.num_params = sum(p.numel() for _, p in self.params)
+
+    def fold_small_grads(self):
+        if self.n > self.n_big:
+            L.accum_fp32_into_bf16(self.G32[: self.n - self.n_big], self.G[self.n_big:])
+            self.G32.zero_()
+
+    def optimizer_step(self, cfg: StepConfig, lr: float, world_size: int = 1):
+        """clip_grad_norm_(max_norm) on the rank-averaged gradient + AdamW (train_utils.py:600-608); zeroes G."""
+        self.sumsq.zero_()
+        L.sumsq(self.G, self.sumsq)
+        self.lr.fill_(lr)
+        self.step_count += 1
+        L.adamw(self.P, self.G, self.m, self.v, sumsq_t=self.sumsq, lr_t=self.lr, step_t=self.step_count, beta1=0.9,
+                beta2=0.999, eps=1e-8, weight_decay=cfg.weight_decay, max_norm=cfg.max_grad_norm,
+                grad_scale=1.0 / world_size, zero_grad=True)
+
+
+def build_labels(cfg: StepConfig, batch, need):
+    """Label tensors for the enabled losses (train_utils.py:171-185, 340-342, 400-402, 429-431, 455-477), bf16, on device.
+    `batch` is a dict (see synthetic_batch); windows are [B, W, ...] with W = sequence_length + future_steps."""
+    S, fs = cfg.sequence_length, cfg.future_steps
+    n_lab = S - cfg.atten_goal
+    out = {}
+    with torch.no_grad():
+        if need.get("image"):
+            for cam, key in (("p", "images_primary"), ("w", "images_wrist")):
+                lab = batch[key][:, fs:fs + n_lab].flatten(0, 1).float()
+                out["image_" + cam] = normalize_patchfied_image(patchify(lab, cfg.patch_size)).to(torch.bfloat16).contiguous()
+            if cfg.flow_as_mask and "tracks" in batch:
+                out["mask_p"], out["mask_w"] = flow_masks(batch["tracks"][:, :n_lab], batch["tracks_gripper"][:, :n_lab])
+        if need.get("depth"):
+            for cam, key in (("p", "depth_primary"), ("w", "depth_wrist")):
+                lab = batch[key][:, fs:fs + n_lab].flatten(0, 1)
+                out["depth_" + cam] = patchify_map(lab, cfg.patch_size).to(torch.bfloat16).contiguous()
+        if need.get("dino"):
+            out["dino_p"] = batch["dino_primary"][:, fs:fs + n_lab].flatten(0, 1).to(torch.bfloat16).contiguous()
+            out["dino_w"] = batch["dino_wrist"][:, fs:fs + n_lab].flatten(0, 1).to(torch.bfloat16).contiguous()
+        if need.get("sam"):
+            out["sam_p"] = batch["sam_primary"][:, fs:fs + n_lab].flatten(0, 1).to(torch.bfloat16).contiguous()
+            out["sam_w"] = batch["sam_wrist"][:, fs:fs + n_lab].flatten(0, 1).to(torch.bfloat16).contiguous()
+        if need.get("traj"):
+            for cam, key in (("p", "tracks"), ("w", "tracks_gripper")):
+                t = batch[key][:, :n_lab]
+                h = w = int(math.sqrt(t.shape[-2]))
+                t = t.reshape(t.shape[0], t.shape[1], h, w, t.shape[-1]).permute(0, 1, 4, 2, 3)
+                t = F.pixel_unshuffle(t, downscale_factor=h // 14)
+                out["traj_" + cam] = t.flatten(3).permute(0, 1, 3, 2).flatten(0, 1).to(torch.bfloat16).contiguous()
+    return out
+
+
+def compute_losses(cfg: StepConfig, outputs, labels, bs, unit_upstream=True):
+    """Weighted loss terms of train_utils.py:158-170,325-337,366-371,423-425,448-450,499-502,585 as fused kernels.
+    Every returned tensor already carries its weight of the total (:585) and 1/accum (:588)."""
+    (arm, gripper, image_pred, _, _, _, depth_pred, traj_pred, dino_pred, sam_pred) = outputs
+    S = cfg.sequence_length
+    n_lab = S - cfg.atten_goal
+    acc = 1.0 / cfg.gradient_accumulation_steps
+    terms = {}
+
+    def trim(t):   # [B*S, 2, P, N, C] -> first S - atten_goal timesteps (train_utils.py:187-189)
+        if n_lab == S:
+            return t
+        return t.reshape(bs, S, *t.shape[1:])[:, :n_lab].reshape(-1, *t.shape[1:])
+
+    if cfg.use_dit_head:
+        terms["action"] = arm * (cfg.loss_arm_action_ratio * acc)
+    elif cfg.loss_action and cfg.action_pred_steps:
+        la = labels["actions"]
+        terms["arm"] = F.smooth_l1_loss(arm[:, :n_lab].float(), la[..., :6].float()) * (cfg.loss_arm_action_ratio * acc)
+        terms["gripper"] = F.binary_cross_entropy(gripper[:, :n_lab].float(), la[..., 6:].float()) * (cfg.loss_gripper_action_ratio * acc)
+    if cfg.loss_image and image_pred is not None:
+        ip = trim(image_pred)
+        w = 0.1 * 0.5 * acc
+        terms["image"] = (ops.mse_loss(ip[:, 0, 0], labels["image_p"], labels.get("mask_p"), w, unit_upstream)
+                          + ops.mse_loss(ip[:, 1, 0], labels["image_w"], labels.get("mask_w"), w, unit_upstream))
+    if cfg.loss_depth and depth_pred is not None:
+        dp = trim(depth_pred)
+        w = 0.001 * 0.5 * acc
+        terms["depth"] = (ops.silog_loss(dp[:, 0, 0], labels["depth_p"], 0.5, w, unit_upstream)
+                          + ops.silog_loss(dp[:, 1, 0], labels["depth_w"], 0.5, w, unit_upstream))
+    if cfg.loss_dino_feat and dino_pred is not None:
+        dp = trim(dino_pred)
+        w = 0.01 * 0.5 * acc
+        terms["dino"] = (ops.cosine_loss(dp[:, 0, 0], labels["dino_p"], w, unit_upstream)
+                         + ops.cosine_loss(dp[:, 1, 0], labels["dino_w"], w, unit_upstream))
+    if cfg.loss_sam_feat and sam_pred is not None:
+        sp = trim(sam_pred)
+        w = 0.01 * 0.5 * acc
+        terms["sam"] = (ops.cosine_loss(sp[:, 0, 0], labels["sam_p"], w, unit_upstream)
+                        + ops.cosine_loss(sp[:, 1, 0], labels["sam_w"], w, unit_upstream))
+    if cfg.loss_trajectory and traj_pred is not None:
+        tp = trim(traj_pred)
+        w = 0.1 * 0.1 * acc
+        terms["traj"] = (ops.mse_loss(tp[:, 0, 0], labels["traj_p"], None, w, unit_upstream)
+                         + ops.mse_loss(tp[:, 1, 0], labels["traj_w"], None, w, unit_upstream))
+    return terms
+
+
+class TrainStep:
+    """One micro-step of train_utils.py:94-608 on device-resident inputs; see module docstring."""
+
+    def __init__(self, model, cfg: StepConfig, world_size=1, process_group=None):
+        self.model, self.cfg = model, cfg
+        self.world_size = world_size
+        self.pg = process_group
+        self.flat = FlatParams(model, cfg)
+        self.micro = 0
+        self.comm_stream = torch.cuda.Stream() if world_size > 1 else None
+        self.last_terms = {}
+
+    def prepare_inputs(self, batch):
+        """train_utils.py:99-145: slices of the window, gripper remap, sliding-window action labels."""
+        cfg = self.cfg
+        S = cfg.sequence_length
+        states = batch["states"]
+        if cfg.gripper_width:
+            input_states = torch.cat([states[..., :6], states[..., -2:]], dim=-1)
+        else:
+            input_states = torch.cat([states[..., :6], states[..., [-1]]], dim=-1)
+            input_states[..., 6:] = torch.div(input_states[..., 6:] + 1, 2, rounding_mode="floor")
+        actions = batch["actions"].clone()
+        actions[..., 6:] = torch.div(actions[..., 6:] + 1, 2, rounding_mode="floor")
+        label_actions = torch.cat([actions[:, j:S - cfg.atten_goal + j, :].unsqueeze(-2)
+                                   for j in range(cfg.action_pred_steps)], dim=-2)
+        text = batch["text"].unsqueeze(1).expand(-1, S, -1)
+        return dict(image_primary=batch["images_primary"][:, :S], image_wrist=batch["images_wrist"][:, :S],
+                    state=input_states[:, :S], text_token=text, action_label=label_actions[:, :S - cfg.atten_goal])
+
+    def forward_backward(self, batch):
+        cfg = self.cfg
+        inp = self.prepare_inputs(batch)
+        need = dict(image=cfg.loss_image, depth=cfg.loss_depth, dino=cfg.loss_dino_feat, sam=cfg.loss_sam_feat,
+                    traj=cfg.loss_trajectory)
+        labels = build_labels(cfg, batch, need)
+        labels["actions"] = inp["action_label"]
+        outputs = self.model(inp["image_primary"], inp["image_wrist"], inp["state"], inp["text_token"], action=None,
+                             action_label=inp["action_label"])
+        terms = compute_losses(cfg, outputs, labels, bs=inp["state"].shape[0])
+        total = None
+        for t in terms.values():
+            total = t if total is None else total + t
+        total.backward()
+        self.flat.fold_small_grads()
+        self.last_terms = {k: v.detach() for k, v in terms.items()}
+        return total.detach()
+
+    def all_reduce_grads(self):
+        """DDP gradient mean (train.py:173): one flat bf16 all-reduce over NCCL on a side stream."""
+        if self.world_size == 1:
+            return
+        import torch.distributed as dist
+        cur = torch.cuda.current_stream()
+        self.comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self.comm_stream):
+            dist.all_reduce(self.flat.G, op=dist.ReduceOp.SUM, group=self.pg)
+        cur.wait_stream(self.comm_stream)
+
+    def __call__(self, batch, lr=None):
+        """Micro-step: returns the (device) loss.  The reference all-reduces and clips EVERY micro-step (§2.2) and steps
+        the optimiser on accumulation boundaries (train_utils.py:599-608)."""
+        cfg = self.cfg
+        loss = self.forward_backward(batch)
+        self.all_reduce_grads()
+        self.micro += 1
+        if self.micro % cfg.gradient_accumulation_steps == 0:
+            self.flat.optimizer_step(cfg, cfg.learning_rate if lr is None else lr, self.world_size)
+        return loss
+
+
+def synthetic_batch(cfg: StepConfig, batch_size, device, seed=1234, heads=None, dtype=torch.bfloat16, pin=False):
+    """Synthetic batch with the collator's output contract (data_utils.py:1395-1397), seeded.
+    Returned as a dict of tensors on `device` (or pinned host tensors with pin=True)."""
+    heads = heads or {}
+    W = cfg.sequence_length + cfg.future_steps
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    B = batch_size
+
+    def rn(*shape, scale=1.0):
+        return (torch.randn(*shape, generator=g) * scale)
+    text = torch.zeros(B, 77, dtype=torch.int32)
+    for b in range(B):
+        k = int(torch.randint(3, 21, (1,), generator=g))
+        text[b, 0] = 49406
+        text[b, 1:1 + k] = torch.randint(1, 49406, (k,), generator=g, dtype=torch.int32)
+        text[b, 1 + k] = 49407
+    states = rn(B, W, 15, scale=0.5)
+    states[..., -1] = (torch.rand(B, W, generator=g) < 0.5).float() * 2 - 1
+    actions = torch.rand(B, W, 7, generator=g) * 2 - 1
+    actions[..., 6] = (torch.rand(B, W, generator=g) < 0.5).float() * 2 - 1
+    out = dict(images_primary=rn(B, W, 3, 224, 224).to(dtype), images_wrist=rn(B, W, 3, 224, 224).to(dtype),
+               text=text.long(), states=states.to(dtype), actions=actions.to(dtype))
+    if heads.get("depth"):
+        out["depth_primary"] = (torch.rand(B, W, 1, 224, 224, generator=g) * 4.9 + 0.1).to(dtype)
+        out["depth_wrist"] = (torch.rand(B, W, 1, 224, 224, generator=g) * 4.9 + 0.1).to(dtype)
+    if heads.get("dino"):
+        out["dino_primary"], out["dino_wrist"] = rn(B, W, 256, 768).to(dtype), rn(B, W, 256, 768).to(dtype)
+    if heads.get("sam"):
+        out["sam_primary"], out["sam_wrist"] = rn(B, W, 256, 256).to(dtype), rn(B, W, 256, 256).to(dtype)
+    if heads.get("traj") or heads.get("flow_mask"):
+        out["tracks"], out["tracks_gripper"] = rn(B, W, 784, 2, scale=2.0).to(dtype), rn(B, W, 784, 2, scale=2.0).to(dtype)
+    if pin:
+        return {k: v.pin_memory() for k, v in out.items()}
+    return {k: v.to(device) for k, v in out.items()}
+
+
+def batch_from_tuple(batch_calvin, device, dtype=torch.bfloat16):
+    """The 13-tuple of the reference's collator (data_utils.py:1395-1397) -> the dict used here (train_utils.py:99-123)."""
+    def mv(t):
+        return None if t is None else t.to(device, dtype=dtype, non_blocking=True)
+    tr = batch_calvin[12] or {}
+    out = dict(images_primary=mv(batch_calvin[0]), text=batch_calvin[1].to(device, non_blocking=True),
+               actions=mv(batch_calvin[2]), images_wrist=mv(batch_calvin[3]), states=mv(batch_calvin[4]))
+    for key, idx in (("depth_primary", 6), ("depth_wrist", 7), ("dino_primary", 8), ("dino_wrist", 9),
+                     ("sam_primary", 10), ("sam_wrist", 11)):
+        if batch_calvin[idx] is not None:
+            out[key] = mv(batch_calvin[idx])
+    if "tracks" in tr:
+        out["tracks"], out["tracks_gripper"] = mv(tr["tracks"]), mv(tr["tracks_gripper"])
+    return out
+
+
+def train_one_epoch_calvin(args, model, epoch, calvin_loader, optimizer, lr_scheduler, device_id, wandb):
+    """Drop-in for reference train_utils.py:59-68.  `model` is the bare DreamVLA or an object with `.module`; `optimizer`
+    may be None (the fused flat AdamW of this package is used) -- `lr_scheduler`, when given, only supplies the lr."""
+    core = model.module if hasattr(model, "module") else model
+    core.train()
+    state = getattr(core, "_dvla_train_step", None)
+    if state is None:
+        import torch.distributed as dist
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        state = TrainStep(core, StepConfig.from_args(args), world_size=world)
+        core._dvla_train_step = state
+    step_time_m, data_time_m = AverageMeter(), AverageMeter()
+    end = time.time()
+    for num_steps, batch_calvin in enumerate(calvin_loader):
+        data_time_m.update(time.time() - end)
+        batch = batch_from_tuple(batch_calvin, device_id)
+        lr = lr_scheduler.get_last_lr()[0] if lr_scheduler is not None else args.learning_rate
+        loss = state(batch, lr=lr)
+        if (num_steps + 1) % args.gradient_accumulation_steps == 0:
+            if lr_scheduler is not None:
+                lr_scheduler.step()
+            step_time_m.update(time.time() - end)
+            end = time.time()
+            if getattr(args, "rank", 0) == 0 and wandb is not None and getattr(args, "report_to_wandb", False):
+                sps = args.gradient_accumulation_steps * args.batch_size * state.world_size / step_time_m.val
+                wandb.log({"calvin_samples_per_second": sps, "loss_calvin": float(loss)}, commit=True)
+    return state

@@ -62,7 +62,8 @@ typedef struct {
   int32_t out_fp32;
   float alpha;
   float dropout_p;        /* 0 disables */
-  uint64_t dropout_seed;  /* mask element index = m*N + n */
+  uint64_t dropout_seed;  /* RNG block = m*ceil(N/8) + n/8, bit n%8 (same convention as dvla_dropout) */
+  const uint64_t* dropout_seed_ptr; /* optional DEVICE counter added to dropout_seed at run time (CUDA-graph replays) */
 } dvla_gemm_args;
 int dvla_gemm(const dvla_gemm_args* args, void* stream);
 
@@ -121,7 +122,8 @@ typedef struct {
   int64_t o_sb, o_ss, o_sh;
   int32_t mask_words;         /* uint32 words per mask row */
   float scale;
-  float dropout_p; uint64_t dropout_seed; /* attention-probability dropout (gpt2.py:272); index = ((b*H+h)*Lq+i)*Lk+j */
+  float dropout_p; uint64_t dropout_seed; /* attention-probability dropout (gpt2.py:272); RNG block = ((b*H+h)*Lq+i)*ceil(Lk/8)+j/8 */
+  const uint64_t* dropout_seed_ptr;       /* optional device counter added to dropout_seed */
 } dvla_attn_fwd_args;
 int dvla_attn_fwd(const dvla_attn_fwd_args* args, void* stream);
 
@@ -138,6 +140,7 @@ typedef struct {
   int32_t mask_words;
   float scale;
   float dropout_p; uint64_t dropout_seed;
+  const uint64_t* dropout_seed_ptr;
 } dvla_attn_bwd_args;
 int dvla_attn_bwd(const dvla_attn_bwd_args* args, void* stream);
 
@@ -155,7 +158,7 @@ int dvla_accum_fp32_into_bf16(const float* src, void* dst_bf16, int64_t n, void*
 /* y = dropout(x) with the same (seed, index) convention as the GEMM epilogue; in place allowed; used for
  * embd dropout (gpt2.py:459) and to re-apply an epilogue dropout mask to dY in the backward. */
 int dvla_dropout(const void* x_bf16, void* y_bf16, int64_t rows, int64_t N, int64_t ldx, int64_t ldy, float p,
-                 uint64_t seed, void* stream);
+                 uint64_t seed, const uint64_t* seed_ptr, void* stream);
 /* dx = dy * act'(pre)  */
 int dvla_act_bwd(const void* dy_bf16, const void* pre_bf16, void* dx_bf16, int64_t n, int32_t act, void* stream);
 

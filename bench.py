@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.1)
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
     ap.add_argument("--layers", type=int, default=24, help=argparse.SUPPRESS)  # debugging only; bench lines use 24
     return ap.parse_args()
 
@@ -136,7 +137,7 @@ def build_model(cfg, device, dropout, layers=None):
 def run_ours(args):
     import torch.distributed as dist
     from dreamvla_b200 import _lib
-    from dreamvla_b200.utils.train_utils import StepConfig, TrainStep, synthetic_batch
+    from dreamvla_b200.utils.train_utils import GraphedTrainStep, StepConfig, TrainStep, synthetic_batch
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -164,6 +165,18 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    eager_step = step
+    graphed = False
+    if not args.no_graph:
+        try:
+            step = GraphedTrainStep(eager_step, batch, warmup=3)
+            batch = step.static
+            graphed = True
+        except Exception as e:  # noqa: BLE001  (same kernels either way; only the launch mechanism differs)
+            print(f"[bench] CUDA-graph capture failed, launching eagerly: {e!r}", file=sys.stderr, flush=True)
+            torch.cuda.synchronize()
+            step = eager_step
+
     # ---- device-resident timing ----
     for _ in range(max(args.warmup, 3)):
         loss = step(batch)
@@ -181,6 +194,8 @@ def run_ours(args):
     sync_all()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - n0
+    if graphed:   # replays do not pass through the host-side counter: kernels recorded per step x replays
+        launches = step.launches_per_step * args.steps
     if sampler:
         sampler.stop_flag.set()
         sampler.join()
@@ -210,11 +225,11 @@ def run_ours(args):
             return out
         _lib.gemm = timed_gemm
         try:
-            step.forward_backward(batch)
+            eager_step.forward_backward(batch)
         finally:
             _lib.gemm = orig
         torch.cuda.synchronize()
-        step.flat.G.zero_()
+        eager_step.flat.G.zero_()
         fl = sum(r[0] for r in recs if r[3])
         tm = sum(r[1].elapsed_time(r[2]) for r in recs if r[3])
         peak, how = measured_peaks()
@@ -230,7 +245,7 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         host = synthetic_batch(scfg, B, dev, seed=1234 + rank, heads=heads, pin=True)
-        dbuf = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+        dbuf = step.static if graphed else {k: torch.empty_like(v, device=dev) for k, v in host.items()}
         loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
         h2d = sum(v.numel() * v.element_size() for v in host.values())
 
@@ -267,9 +282,9 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": cfg["name"], "per_gpu_batch": B, "global_batch": B * world,
                        "seq_len": cfg["model"]["sequence_length"], "parallelism": f"dp{world}",
-                       "dropout": args.dropout, "layers": args.layers,
+                       "dropout": args.dropout, "layers": args.layers, "cuda_graph": graphed,
                        "l2": "inputs+weights+activations per step >> 126 MB L2 (1.3 GB of bf16 weights re-read every step); no explicit flush",
-                       "trainable_params": step.flat.num_params, "final_loss": final_loss},
+                       "trainable_params": eager_step.flat.num_params, "final_loss": final_loss},
             "clocks": sampler.summary() if sampler else None,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
         }

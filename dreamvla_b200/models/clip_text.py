@@ -4,7 +4,8 @@ Boundary input of the hot path (dreamvla_model.py:643-649): fr
 installable offline, so `load()` returns a random-initialised tower with CLIP's parameter names
 (token_embedding, positional_embedding, transformer.resblocks.N.{ln_1, attn.in_proj_weight/bias, attn.out_proj,
 ln_2, mlp.c_fc, mlp.c_proj}, ln_final, text_projection) so that a real CLIP state_dict loads with strict=False.
-Exact win kept from SURVEY k17: identical sentences are encoded once (the reference encodes each S times).
+Exact win kept from SURVEY k17: a sentence repeated over the window (text_token expanded along S, as both the train
+loop and the rollout wrappers do) is encoded once by DreamVLA.forward (the reference encodes it S times).
 """
 from __future__ import annotations
 
@@ -87,8 +88,8 @@ class CLIPTextTower(nn.Module):
 
     @torch.no_grad()
     def encode_text(self, text):
-        """text int [n, 77] -> [n, embed_dim].  Duplicate rows are encoded once."""
-        uniq, inverse = torch.unique(text, dim=0, return_inverse=True)
+        """text int [n, 77] -> [n, embed_dim].  (No host sync: CUDA-graph capturable.)"""
+        uniq = text
         x = self.token_embedding(uniq) + self.positional_embedding
         if self._mask is None or self._mask.bits.device != x.device:
             self._mask = ops.AttnMask.causal(self.context_length, x.device)
@@ -96,8 +97,7 @@ class CLIPTextTower(nn.Module):
             x = blk(x, self._mask)
         x = self.ln_final(x)
         eot = x[torch.arange(x.shape[0], device=x.device), uniq.argmax(dim=-1)]
-        feats = ops.linear(eot, self.text_projection, None, weight_kn=True)
-        return feats[inverse]
+        return ops.linear(eot, self.text_projection, None, weight_kn=True)
 
 
 def load(name="ViT-B/32", device="cpu", seed=20240607):

@@ -376,7 +376,8 @@ class DreamVLA(nn.Module):
                 mode="train", diffusion_noise=None, diffusion_timestep=None, diffusion_drop_ids=None, sample_noise=None):
         """Reference :609-991.  The four trailing keyword arguments inject the tensors the reference samples inside
         forward (action_model.py:59-60, models.py:83, dreamvla_model.py:944) so parity tests can line them up."""
-        if self.training and self.phase == "pretrain":       # :610-628 mask regenerated each forward (np.random)
+        if self.training and self.phase == "pretrain" and self.mask_l_obs_ratio > 0 and self.atten_only_obs:
+            # :610-628 mask regenerated each forward; only the np.random column drop (:55-59) makes it differ
             self.attention_mask = nn.Parameter(self._make_mask().to(self.attention_mask.device), requires_grad=False)
         B, S, _ = state.shape
         D = self.hidden_dim
@@ -388,7 +389,11 @@ class DreamVLA(nn.Module):
 
         # ---- text (:643-653) ----
         with torch.no_grad():
-            text_feature = self.clip_model.encode_text(text_token.flatten(0, 1)).to(dt)
+            if text_token.stride(1) == 0 and S > 1:     # one sentence expanded over the window: encode once
+                tf = self.clip_model.encode_text(text_token[:, 0].contiguous()).to(dt)
+                text_feature = tf.unsqueeze(1).expand(B, S, -1).reshape(B * S, -1)
+            else:
+                text_feature = self.clip_model.encode_text(text_token.flatten(0, 1)).to(dt)
         text_embedding = self.text_projector(text_feature).view(B, S, -1, D)
 
         # ---- state (:656-664) ----

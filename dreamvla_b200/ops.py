@@ -81,9 +81,7 @@ class _Linear(torch.autograd.Function):
     def forward(ctx, x, weight, bias, residual, act, weight_kn, dropout_p, alpha):
         x2 = _as2d(_bf16c(x))
         N = weight.shape[1] if weight_kn else weight.shape[0]
-        need_grad = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or
-                                                 (bias is not None and bias.requires_grad) or
-                                                 (residual is not None and residual.requires_grad))
+        need_grad = any(ctx.needs_input_grad)      # (Function.forward runs with grad mode off; this is the signal)
         aux = None
         if act != 0 and need_grad:
             aux = torch.empty((x2.shape[0], N), device=x2.device, dtype=torch.bfloat16)
@@ -136,7 +134,7 @@ class _LayerNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, eps):
         x2 = _as2d(_bf16c(x))
-        need = torch.is_grad_enabled() and (x.requires_grad or (gamma is not None and gamma.requires_grad))
+        need = any(ctx.needs_input_grad)
         y, mean, rstd = L.layernorm_fwd(x2, gamma, beta, eps, save_stats=need)
         if need:
             ctx.save_for_backward(x2, mean, rstd)
@@ -199,7 +197,7 @@ class AttnMask:
 class _Attention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, scale, mask, dropout_p):
-        need = torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad)
+        need = any(ctx.needs_input_grad)
         seed = next_seed() if dropout_p > 0 else 0
         bits = mask.bits if mask is not None else None
         flags = mask.flags if mask is not None else None
@@ -243,7 +241,7 @@ class _FusedQKVAttention(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, qkv, scale, mask, dropout_p):
-        need = torch.is_grad_enabled() and qkv.requires_grad
+        need = any(ctx.needs_input_grad)
         seed = next_seed() if dropout_p > 0 else 0
         q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
         o, lse = L.attn_fwd(q, k, v, scale, mask.bits if mask is not None else None,
@@ -309,7 +307,7 @@ class _MSELoss(_LossBase):
     def forward(ctx, pred, label, row_mask, weight, unit_upstream):
         p2, l2 = _as2d(_bf16c(pred)), _as2d(_bf16c(label))
         loss = torch.zeros(1, device=pred.device, dtype=torch.float32)
-        dpred = torch.empty_like(p2) if pred.requires_grad else None
+        dpred = torch.empty_like(p2) if ctx.needs_input_grad[0] else None
         L.mse_loss(p2, l2, row_mask, weight, loss, dpred)
         if dpred is not None:
             ctx.save_for_backward(dpred)
@@ -327,7 +325,7 @@ class _CosineLoss(_LossBase):
     def forward(ctx, pred, label, weight, unit_upstream):
         p2, l2 = _as2d(_bf16c(pred)), _as2d(_bf16c(label))
         loss = torch.zeros(1, device=pred.device, dtype=torch.float32)
-        dpred = torch.empty_like(p2) if pred.requires_grad else None
+        dpred = torch.empty_like(p2) if ctx.needs_input_grad[0] else None
         L.cosine_loss(p2, l2, weight, loss, dpred)
         if dpred is not None:
             ctx.save_for_backward(dpred)
@@ -345,7 +343,7 @@ class _SiLogLoss(_LossBase):
     def forward(ctx, pred, label, lambd, weight, unit_upstream):
         p, l = _bf16c(pred), _bf16c(label)
         loss = torch.zeros(1, device=pred.device, dtype=torch.float32)
-        dpred = torch.empty_like(p) if pred.requires_grad else None
+        dpred = torch.empty_like(p) if ctx.needs_input_grad[0] else None
         L.silog_loss(p, l, lambd, weight, loss, dpred)
         if dpred is not None:
             ctx.save_for_backward(dpred)

@@ -200,11 +200,13 @@ class FlatParams:
             L.accum_fp32_into_bf16(self.G32[: self.n - self.n_big], self.G[self.n_big:])
             self.G32.zero_()
 
-    def optimizer_step(self, cfg: StepConfig, lr: float, world_size: int = 1):
-        """clip_grad_norm_(max_norm) on the rank-averaged gradient + AdamW (train_utils.py:600-608); zeroes G."""
+    def optimizer_step(self, cfg: StepConfig, lr: float | None, world_size: int = 1):
+        """clip_grad_norm_(max_norm) on the rank-averaged gradient + AdamW (train_utils.py:600-608); zeroes G.
+        lr=None keeps the device-resident lr (set outside a captured CUDA graph)."""
         self.sumsq.zero_()
         L.sumsq(self.G, self.sumsq)
-        self.lr.fill_(lr)
+        if lr is not None:
+            self.lr.fill_(lr)
         self.step_count += 1
         L.adamw(self.P, self.G, self.m, self.v, sumsq_t=self.sumsq, lr_t=self.lr, step_t=self.step_count, beta1=0.9,
                 beta2=0.999, eps=1e-8, weight_decay=cfg.weight_decay, max_norm=cfg.max_grad_norm,
@@ -355,12 +357,56 @@ class TrainStep:
         """Micro-step: returns the (device) loss.  The reference all-reduces and clips EVERY micro-step (§2.2) and steps
         the optimiser on accumulation boundaries (train_utils.py:599-608)."""
         cfg = self.cfg
-        loss = self.forward_backward(batch)
-        self.all_reduce_grads()
+        self.flat.lr.fill_(cfg.learning_rate if lr is None else lr)
+        loss = self.micro_step(batch)
         self.micro += 1
         if self.micro % cfg.gradient_accumulation_steps == 0:
-            self.flat.optimizer_step(cfg, cfg.learning_rate if lr is None else lr, self.world_size)
+            self.flat.optimizer_step(cfg, None, self.world_size)
         return loss
+
+    def micro_step(self, batch):
+        ops.seed_counter(self.flat.P.device).add_(1)        # fresh dropout masks every step, also under graph replay
+        loss = self.forward_backward(batch)
+        self.all_reduce_grads()
+        return loss
+
+
+class GraphedTrainStep:
+    """The whole micro-step (forward, losses, backward, all-reduce) and the optimiser step captured as two CUDA graphs:
+    the reference issues ~4-5 k kernel launches per step from Python; a replay is one launch.  Inputs are copied into
+    static device buffers (that copy IS the H2D transfer when the source is pinned host memory)."""
+
+    def __init__(self, step: TrainStep, example_batch, warmup=3):
+        self.step = step
+        self.static = {k: v.clone() for k, v in example_batch.items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                       # real steps: allocator pools, caches, lazy tables
+                step(self.static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        n0 = L.launch_count()
+        self.g_micro = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_micro):
+            self.loss = step.micro_step(self.static)
+        self.g_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_opt, pool=self.g_micro.pool()):
+            step.flat.optimizer_step(step.cfg, None, step.world_size)
+        self.launches_per_step = L.launch_count() - n0      # libdvla kernels recorded in the two graphs
+
+    def __call__(self, batch, lr=None):
+        st = self.step
+        if batch is not self.static:
+            for k, v in batch.items():
+                self.static[k].copy_(v, non_blocking=True)
+        if lr is not None:
+            st.flat.lr.fill_(lr)
+        self.g_micro.replay()
+        st.micro += 1
+        if st.micro % st.cfg.gradient_accumulation_steps == 0:
+            self.g_opt.replay()
+        return self.loss
 
 
 def synthetic_batch(cfg: StepConfig, batch_size, device, seed=1234, heads=None, dtype=torch.bfloat16, pin=False):

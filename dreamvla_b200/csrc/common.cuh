@@ -179,9 +179,22 @@ __device__ __forceinline__ float warp_max(float v) {
 // Activations (fp32 math).  Ids are part of the C ABI (include/dvla.h).
 enum Act : int { ACT_NONE = 0, ACT_GELU_ERF = 1, ACT_GELU_TANH = 2, ACT_QUICK_GELU = 3, ACT_RELU = 4, ACT_SILU = 5 };
 
+// erf with |abs error| <= 1.5e-7 (Abramowitz & Stegun 7.1.26): 5 FMA + rcp + exp -- the GEMM epilogue is ALU-bound for
+// K ~ 1024 with libdevice erff (~25 instructions per element).
+__device__ __forceinline__ float fast_erf(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float r = 1.0f - p * t * __expf(-ax * ax);
+  return copysignf(r, x);
+}
+
 __device__ __forceinline__ float act_fwd(float x, int act) {
   switch (act) {
-    case ACT_GELU_ERF: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+    case ACT_GELU_ERF: return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f));
     case ACT_GELU_TANH: {  // 0.5x(1+tanh(u)) == x*sigmoid(2u)
       float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
       return x / (1.0f + __expf(-2.0f * u));
@@ -192,11 +205,39 @@ __device__ __forceinline__ float act_fwd(float x, int act) {
     default: return x;
   }
 }
+// Apply an activation to n values with the switch hoisted out of the element loop.
+template <int N>
+__device__ __forceinline__ void act_fwd_n(float (&v)[N], int act) {
+  switch (act) {
+    case ACT_GELU_ERF:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = act_fwd(v[j], ACT_GELU_ERF);
+      break;
+    case ACT_GELU_TANH:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = act_fwd(v[j], ACT_GELU_TANH);
+      break;
+    case ACT_QUICK_GELU:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = act_fwd(v[j], ACT_QUICK_GELU);
+      break;
+    case ACT_RELU:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = fmaxf(v[j], 0.f);
+      break;
+    case ACT_SILU:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = act_fwd(v[j], ACT_SILU);
+      break;
+    default: break;
+  }
+}
+
 // d act(x) / dx evaluated at the pre-activation x.
 __device__ __forceinline__ float act_bwd(float x, int act) {
   switch (act) {
     case ACT_GELU_ERF: {
-      float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+      float cdf = 0.5f * (1.0f + fast_erf(x * 0.70710678118654752f));
       float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
       return cdf + x * pdf;
     }

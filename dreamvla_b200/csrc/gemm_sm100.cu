@@ -32,7 +32,7 @@ struct GemmParams {
   int M, N, K;
   long long ldo, ldr, ld_aux;
   int num_m_tiles, num_n_tiles, num_k_blocks;
-  int act, out_fp32, vec_ok;
+  int act, out_fp32, vec_ok, staged_ok;
   float alpha;
   float drop_scale;        // 1/(1-p_eff), 0 => dropout disabled
   uint32_t drop_thresh;    // round(p*65536)
@@ -47,7 +47,8 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES;
+  static constexpr int STAGING_BYTES = NUM_EPI_WARPS * 4096;   // per epilogue warp: 32 rows x 128 B
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + BAR_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
@@ -100,8 +101,7 @@ __device__ __forceinline__ void epilogue8(float (&v)[8], int row, int col, const
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] *= act_bwd(x[j], p.act);
   } else if (p.act != ACT_NONE) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = act_fwd(v[j], p.act);
+    act_fwd_n<8>(v, p.act);
   }
   if (p.drop_scale != 0.f) {
     // element index = row*N + col; 8-element RNG blocks need col%8==0 alignment relative to row*N -> use (row*N+col)/8
@@ -157,6 +157,112 @@ __device__ __forceinline__ void epilogue8(float (&v)[8], int row, int col, const
   }
 }
 
+// ---- staged epilogue: per-warp 32 x 128 B smem panel, 16-byte chunk c of row r stored at chunk c ^ (r & 7) ------------
+// The thread<->row TMEM layout gives each lane 64 contiguous bf16 of ONE row; writing those straight to global costs 32
+// L1 wavefronts per store instruction.  Staging through this swizzled panel turns every global access of the epilogue
+// (output, pre-activation copy, residual) into full 128-byte lines: 4 rows per instruction.
+__device__ __forceinline__ uint4* stage_ptr(uint8_t* base, int row, int chunk) {
+  return reinterpret_cast<uint4*>(base + row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+__device__ __forceinline__ void stage_write_row(uint8_t* base, int lane, const float (&v)[64]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    *stage_ptr(base, lane, c) = make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
+                                           pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
+}
+// panel (rows row0.., cols col0..col0+63) <-> global [*, ld] bf16; rows >= M and 8-col groups >= N are skipped
+__device__ __forceinline__ void stage_flush(uint8_t* base, int lane, bf16* g, long long ld, int row0, int col0, int M, int N) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + (lane >> 3), c = lane & 7;
+    if (row0 + r < M && col0 + c * 8 < N)
+      *reinterpret_cast<uint4*>(g + static_cast<long long>(row0 + r) * ld + col0 + c * 8) = *stage_ptr(base, r, c);
+  }
+}
+__device__ __forceinline__ void stage_load(uint8_t* base, int lane, const bf16* g, long long ld, int row0, int col0, int M, int N) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + (lane >> 3), c = lane & 7;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (row0 + r < M && col0 + c * 8 < N)
+      val = *reinterpret_cast<const uint4*>(g + static_cast<long long>(row0 + r) * ld + col0 + c * 8);
+    *stage_ptr(base, r, c) = val;
+  }
+}
+
+// one 64-column panel of one warp: v[64] = this lane's row (row0 + lane), columns col0 .. col0+63
+__device__ __forceinline__ void epilogue_panel_staged(float (&v)[64], uint8_t* stage, int lane, int row0, int col0,
+                                                      const GemmParams& p) {
+  const int row = row0 + lane;
+  if (p.alpha != 1.0f) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) v[j] *= p.alpha;
+  }
+  if (p.bias) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (col0 + c * 8 < p.N) {
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + c * 8));
+        float2 f;
+        f = unpack_bf16x2(b.x); v[8 * c] += f.x; v[8 * c + 1] += f.y;
+        f = unpack_bf16x2(b.y); v[8 * c + 2] += f.x; v[8 * c + 3] += f.y;
+        f = unpack_bf16x2(b.z); v[8 * c + 4] += f.x; v[8 * c + 5] += f.y;
+        f = unpack_bf16x2(b.w); v[8 * c + 6] += f.x; v[8 * c + 7] += f.y;
+      }
+    }
+  }
+  if (p.aux_out) {
+    stage_write_row(stage, lane, v);
+    __syncwarp();
+    stage_flush(stage, lane, p.aux_out, p.ld_aux, row0, col0, p.M, p.N);
+    __syncwarp();
+  }
+  if (p.aux_in) {
+    stage_load(stage, lane, p.aux_in, p.ld_aux, row0, col0, p.M, p.N);
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 a = *stage_ptr(stage, lane, c);
+      float2 f;
+      f = unpack_bf16x2(a.x); v[8 * c] *= act_bwd(f.x, p.act); v[8 * c + 1] *= act_bwd(f.y, p.act);
+      f = unpack_bf16x2(a.y); v[8 * c + 2] *= act_bwd(f.x, p.act); v[8 * c + 3] *= act_bwd(f.y, p.act);
+      f = unpack_bf16x2(a.z); v[8 * c + 4] *= act_bwd(f.x, p.act); v[8 * c + 5] *= act_bwd(f.y, p.act);
+      f = unpack_bf16x2(a.w); v[8 * c + 6] *= act_bwd(f.x, p.act); v[8 * c + 7] *= act_bwd(f.y, p.act);
+    }
+    __syncwarp();
+  } else if (p.act != ACT_NONE) {
+    act_fwd_n<64>(v, p.act);
+  }
+  if (p.drop_scale != 0.f) {
+    const uint64_t seed = p.drop_seed + (p.drop_seed_ptr ? __ldg(p.drop_seed_ptr) : 0ull);
+    const uint64_t blk0 = static_cast<uint64_t>(row) * static_cast<uint64_t>((p.N + 7) >> 3) + (col0 >> 3);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint32_t keep = dropout_keep8(seed, blk0 + c, p.drop_thresh);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[8 * c + j] = ((keep >> j) & 1u) ? v[8 * c + j] * p.drop_scale : 0.f;
+    }
+  }
+  if (p.residual) {
+    stage_load(stage, lane, reinterpret_cast<const bf16*>(p.residual), p.ldr, row0, col0, p.M, p.N);
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 a = *stage_ptr(stage, lane, c);
+      float2 f;
+      f = unpack_bf16x2(a.x); v[8 * c] += f.x; v[8 * c + 1] += f.y;
+      f = unpack_bf16x2(a.y); v[8 * c + 2] += f.x; v[8 * c + 3] += f.y;
+      f = unpack_bf16x2(a.z); v[8 * c + 4] += f.x; v[8 * c + 5] += f.y;
+      f = unpack_bf16x2(a.w); v[8 * c + 6] += f.x; v[8 * c + 7] += f.y;
+    }
+    __syncwarp();
+  }
+  stage_write_row(stage, lane, v);
+  __syncwarp();
+  stage_flush(stage, lane, reinterpret_cast<bf16*>(p.out), p.ldo, row0, col0, p.M, p.N);
+  __syncwarp();
+}
+
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -166,7 +272,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -272,6 +379,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row = m0 + q * 32 + lane;
       const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       constexpr int CHUNKS = BN / 2 / 32;
+      if (p.staged_ok) {
+        uint8_t* stage = staging + (warp - 2) * 4096;
+        constexpr int PANELS = BN / 2 / 64;
+#pragma unroll 1
+        for (int pi = 0; pi < PANELS; ++pi) {
+          const int c = half * (BN / 2) + pi * 64;
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(t_lane + c, r0);
+          tmem_ld_32x32(t_lane + c + 32, r1);
+          tmem_ld_wait();
+          if (pi == PANELS - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+          if (n0 + c < p.N) {      // warp-uniform
+            float v[64];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
+            epilogue_panel_staged(v, stage, lane, m0 + q * 32, n0 + c, p);
+          }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_ph ^= 1;
+        continue;
+      }
 #pragma unroll 1
       for (int ci = 0; ci < CHUNKS; ++ci) {
         const int c = half * (BN / 2) + ci * 32;
@@ -433,6 +566,7 @@ int gemm_dispatch(const dvla_gemm_args* a, cudaStream_t stream) {
              (!a->residual || (aligned16(a->residual) && a->ldr % oal == 0)) &&
              (!a->aux_out || (aligned16(a->aux_out) && a->ld_aux % 8 == 0)) &&
              (!a->aux_in || (aligned16(a->aux_in) && a->ld_aux % 8 == 0));
+  p.staged_ok = p.vec_ok && !a->out_fp32 && (a->N % 8 == 0);
   p.num_m_tiles = (p.M + BM - 1) / BM;
   p.num_k_blocks = (p.K + BK - 1) / BK;
 

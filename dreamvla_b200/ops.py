@@ -172,7 +172,9 @@ class AttnMask:
     """Bit-matrix visibility mask + per-tile flags, built once per mask (dreamvla_model.py:25-66 semantics:
     additive 0 -> visible, -inf -> hidden).  Shared across batch and heads."""
 
-    def __init__(self, visible_bool: torch.Tensor, device):
+    @staticmethod
+    def pack_bits(visible_bool: torch.Tensor) -> torch.Tensor:
+        """[Lq, Lk] bool -> [Lq, ceil(Lk/32)] int32; bit (j % 32) of word (j // 32) set <=> pair (i, j) visible."""
         assert visible_bool.dim() == 2 and visible_bool.dtype == torch.bool
         Lq, Lk = visible_bool.shape
         words = (Lk + 31) // 32
@@ -180,10 +182,12 @@ class AttnMask:
         padded[:, :Lk] = visible_bool.cpu()
         w = padded.view(Lq, words, 32).to(torch.int64)
         bits = (w << torch.arange(32, dtype=torch.int64)).sum(-1)
-        bits = torch.where(bits >= 2 ** 31, bits - 2 ** 32, bits).to(torch.int32)
-        self.Lq, self.Lk = Lq, Lk
-        self.bits = bits.to(device).contiguous()
-        self.flags = L.attn_mask_tiles(self.bits, Lq, Lk)
+        return torch.where(bits >= 2 ** 31, bits - 2 ** 32, bits).to(torch.int32)
+
+    def __init__(self, visible_bool: torch.Tensor, device):
+        self.Lq, self.Lk = visible_bool.shape
+        self.bits = self.pack_bits(visible_bool).to(device).contiguous()
+        self.flags = L.attn_mask_tiles(self.bits, self.Lq, self.Lk)
 
     @staticmethod
     def from_additive(mask_float: torch.Tensor, device):

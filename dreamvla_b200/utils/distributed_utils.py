@@ -1,0 +1,45 @@
+"""Rank discovery and process-group setup -- mirror of reference utils/distributed_utils.py:25-47,103-161 (env-var based,
+one process per GPU, NCCL).  Rendezvous defaults to 127.0.0.1."""
+from __future__ import annotations
+
+import datetime
+import os
+
+import torch
+
+
+def world_info_from_env():
+    local_rank = 0
+    for v in ("LOCAL_RANK", "MPI_LOCALRANKID", "SLURM_LOCALID", "OMPI_COMM_WORLD_LOCAL_RANK"):
+        if v in os.environ:
+            local_rank = int(os.environ[v])
+            break
+    global_rank = 0
+    for v in ("RANK", "PMI_RANK", "SLURM_PROCID", "OMPI_COMM_WORLD_RANK"):
+        if v in os.environ:
+            global_rank = int(os.environ[v])
+            break
+    world_size = 1
+    for v in ("WORLD_SIZE", "PMI_SIZE", "SLURM_NTASKS", "OMPI_COMM_WORLD_SIZE"):
+        if v in os.environ:
+            world_size = int(os.environ[v])
+            break
+    return local_rank, global_rank, world_size
+
+
+def init_distributed_device(args):
+    args.distributed = False
+    if not hasattr(args, "world_size"):
+        args.local_rank, args.rank, args.world_size = world_info_from_env()
+    if not torch.cuda.is_available():
+        raise RuntimeError("dreamvla_b200 needs a CUDA device (B200); there is no CPU path")
+    device = torch.device("cuda", args.local_rank)
+    torch.cuda.set_device(device)
+    if args.world_size > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        torch.distributed.init_process_group(backend=getattr(args, "dist_backend", "nccl"), device_id=device,
+                                             timeout=datetime.timedelta(seconds=7200))
+        args.distributed = True
+    args.device = device
+    return device

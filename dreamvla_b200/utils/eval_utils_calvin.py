@@ -1,0 +1,56 @@
+"""Action-inference wrapper -- mirror of reference utils/eval_utils_calvin.py:48-147 (`ModelWrapper.step`) and of the
+LIBERO variant's window handling (utils/eval_utils_libero.py:94-179), without the simulators (out of scope).
+
+Semantics kept: growing-then-sliding window of `history_len` frames, window padded by repeating the last frame, the
+instruction tokens repeated over the window, full-window `mode='test'` forward every env step, gripper thresholding and
+selection of row `num_step-1` (or the last row once the window is full).  Inputs are already-preprocessed tensors
+(CLIP image preprocessing / tokenisation are data-side).
+"""
+from __future__ import annotations
+
+from collections import deque
+
+import torch
+
+
+class ModelWrapper:
+    def __init__(self, model, cast_dtype=torch.bfloat16, history_len=10, action_pred_steps=3, device="cuda"):
+        self.model = model.module if hasattr(model, "module") else model
+        self.cast_type = cast_dtype
+        self.history_len = history_len
+        self.action_pred_steps = action_pred_steps
+        self.device = device
+        self.reset()
+
+    def reset(self):
+        self.img_queue = deque(maxlen=self.history_len)
+        self.gripper_queue = deque(maxlen=self.history_len)
+        self.state_queue = deque(maxlen=self.history_len)
+        self.text_token = None
+
+    @torch.no_grad()
+    def step(self, image_static, image_gripper, robot_obs, text_tokens, sample_noise=None):
+        """image_* [3,224,224] preprocessed, robot_obs [15], text_tokens int [77] -> action [7] (fp16 numpy like the reference)."""
+        dev = self.device
+        self.img_queue.append(image_static.to(dev, self.cast_type).view(1, 1, 3, 224, 224))
+        self.gripper_queue.append(image_gripper.to(dev, self.cast_type).view(1, 1, 3, 224, 224))
+        st = robot_obs.to(dev, self.cast_type).view(1, 1, -1)
+        self.state_queue.append(torch.cat([st[..., :6], st[..., [-1]]], dim=-1))
+        if self.text_token is None:                              # frozen for the episode (eval_utils_calvin.py:110-113)
+            self.text_token = text_tokens.to(dev).view(1, 1, 77).expand(1, self.history_len, 77)
+        image_primary = torch.cat(list(self.img_queue), dim=1)
+        image_wrist = torch.cat(list(self.gripper_queue), dim=1)
+        state = torch.cat(list(self.state_queue), dim=1)
+        num_step = image_primary.shape[1]
+        if num_step < self.history_len:
+            pad = self.history_len - num_step
+            image_primary = torch.cat([image_primary, image_primary[:, -1:].expand(-1, pad, -1, -1, -1)], dim=1)
+            image_wrist = torch.cat([image_wrist, image_wrist[:, -1:].expand(-1, pad, -1, -1, -1)], dim=1)
+            state = torch.cat([state, state[:, -1:].expand(-1, pad, -1)], dim=1)
+        out = self.model(image_primary=image_primary, image_wrist=image_wrist, state=state, text_token=self.text_token,
+                         action=None, mode="test", sample_noise=sample_noise)
+        arm_action, gripper_action = out[0], out[1]
+        action = torch.cat((arm_action[0, :, 0, :].float(), (gripper_action[0, :, 0, :] > 0.5).float()), dim=-1)
+        action[:, -1] = (action[:, -1] - 0.5) * 2
+        row = num_step - 1 if num_step < self.history_len else -1
+        return action[row].to(torch.float16).cpu().numpy()

@@ -294,6 +294,22 @@ def compute_losses(cfg: StepConfig, outputs, labels, bs, unit_upstream=True):
     return terms
 
 
+def all_reduce_flat(G, world_size, group=None, comm_stream=None):
+    """SUM all-reduce of the flat gradient buffer (the 1/world of DDP's mean is applied later as `grad_scale` inside the
+    clip+AdamW kernel).  On CUDA it runs on `comm_stream`, ordered after the producer stream and before its consumers."""
+    if world_size == 1:
+        return
+    import torch.distributed as dist
+    if comm_stream is None or not G.is_cuda:
+        dist.all_reduce(G, op=dist.ReduceOp.SUM, group=group)
+        return
+    cur = torch.cuda.current_stream()
+    comm_stream.wait_stream(cur)
+    with torch.cuda.stream(comm_stream):
+        dist.all_reduce(G, op=dist.ReduceOp.SUM, group=group)
+    cur.wait_stream(comm_stream)
+
+
 class TrainStep:
     """One micro-step of train_utils.py:94-608 on device-resident inputs; see module docstring."""
 
@@ -344,14 +360,7 @@ class TrainStep:
 
     def all_reduce_grads(self):
         """DDP gradient mean (train.py:173): one flat bf16 all-reduce over NCCL on a side stream."""
-        if self.world_size == 1:
-            return
-        import torch.distributed as dist
-        cur = torch.cuda.current_stream()
-        self.comm_stream.wait_stream(cur)
-        with torch.cuda.stream(self.comm_stream):
-            dist.all_reduce(self.flat.G, op=dist.ReduceOp.SUM, group=self.pg)
-        cur.wait_stream(self.comm_stream)
+        all_reduce_flat(self.flat.G, self.world_size, self.pg, self.comm_stream)
 
     def __call__(self, batch, lr=None):
         """Micro-step: returns the (device) loss.  The reference all-reduces and clips EVERY micro-step (§2.2) and steps

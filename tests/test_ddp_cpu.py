@@ -1,0 +1,55 @@
+"""world_size-2 gloo test of the data-parallel exchange step (host-side logic of TrainStep.all_reduce_grads): one flat
+SUM all-reduce, mean folded in afterwards as grad_scale = 1/world -- must equal the DDP gradient mean (train.py:173)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dreamvla_b200.utils.train_utils import all_reduce_flat
+    g = torch.Generator().manual_seed(100 + rank)
+    G = torch.randn(1000, generator=g).to(torch.bfloat16)       # this rank's local flat gradient
+    local = G.float().clone()
+    all_reduce_flat(G, world_size=world, group=None, comm_stream=None)
+    gathered = [torch.zeros(1000) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    mean = torch.stack(gathered).mean(0)
+    got = G.float() / world                                        # 1/world is applied by the AdamW kernel (grad_scale)
+    ret[rank] = float((got - mean).abs().max())
+    # every rank must hold the same reduced buffer -> identical optimiser updates
+    ref = [torch.zeros(1000, dtype=torch.bfloat16) for _ in range(world)]
+    dist.all_gather(ref, G)
+    ret[10 + rank] = bool(all(torch.equal(ref[0], r) for r in ref))
+    dist.destroy_process_group()
+
+
+def test_flat_allreduce_is_ddp_mean():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    for r in range(world):
+        assert ret[r] < 0.05, ret[r]          # bf16 sum rounding
+        assert ret[10 + r]
+
+
+def test_rank_seeds_shard_the_data():
+    from dreamvla_b200.utils.train_utils import StepConfig, synthetic_batch
+    cfg = StepConfig(sequence_length=2)
+    a = synthetic_batch(cfg, 1, "cpu", seed=1234 + 0)
+    b = synthetic_batch(cfg, 1, "cpu", seed=1234 + 1)
+    assert not torch.equal(a["images_primary"], b["images_primary"])
+    assert a["images_primary"].shape == (1, 5, 3, 224, 224) and a["text"].shape == (1, 77)

@@ -294,6 +294,19 @@ def run_ours(args):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+def usable_cores(cap=32):
+    """Host threads actually available to this process: affinity mask and cgroup CPU quota, capped (OpenMP scaling of
+    the many small fp32 ops of this workload collapses beyond a few dozen threads)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(per))))
+    except Exception:  # noqa: BLE001
+        pass
+    return max(1, min(n, cap))
+
+
 def cpu_baseline(args, steps=1, warm=0, budget_s=150.0):
     """The reference's algorithm (oracle port, fp32) on the host cores: fwd + losses + bwd + clip + AdamW, B = 1 window."""
     from oracle import dreamvla_oracle as O
@@ -303,7 +316,7 @@ def cpu_baseline(args, steps=1, warm=0, budget_s=150.0):
     mk = dict(cfg["model"], batch=1, weight_seed=1, input_seed=2)
     if args.layers is not None:
         mk["transformer_layers"] = args.layers
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     sd = synth.synth_state_dict(build_template(mk), 1)
     frozen = ("vision_encoder.", "clip_model.", "attention_mask", "position_embedding")

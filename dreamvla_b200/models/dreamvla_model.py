@@ -400,8 +400,9 @@ class DreamVLA(nn.Module):
         st = state.flatten(0, 1).to(dt)
         arm_state_feature = self.arm_state_encoder(st[:, :6].contiguous())
         if not self.gripper_width:
-            idx = torch.where(st[:, 6:].flatten() < 1, 0, 1)
-            gripper_in = F.one_hot(idx, num_classes=2).to(dt)
+            idx = (st[:, 6:].flatten() >= 1).long()      # 0 if < 1 else 1 (no host scalars: graph-capturable)
+            idxf = idx.to(dt)
+            gripper_in = torch.stack((1 - idxf, idxf), dim=1)      # == F.one_hot(idx, 2), without its value check
         else:
             gripper_in = st[:, 6:].contiguous()
         gripper_state_feature = self.gripper_state_encoder(gripper_in)

@@ -35,7 +35,7 @@ class ModelWrapper:
         self.img_queue.append(image_static.to(dev, self.cast_type).view(1, 1, 3, 224, 224))
         self.gripper_queue.append(image_gripper.to(dev, self.cast_type).view(1, 1, 3, 224, 224))
         st = robot_obs.to(dev, self.cast_type).view(1, 1, -1)
-        self.state_queue.append(torch.cat([st[..., :6], st[..., [-1]]], dim=-1))
+        self.state_queue.append(torch.cat([st[..., :6], st[..., -1:]], dim=-1))
         if self.text_token is None:                              # frozen for the episode (eval_utils_calvin.py:110-113)
             self.text_token = text_tokens.to(dev).view(1, 1, 77).expand(1, self.history_len, 77)
         image_primary = torch.cat(list(self.img_queue), dim=1)

@@ -330,7 +330,7 @@ class TrainStep:
         if cfg.gripper_width:
             input_states = torch.cat([states[..., :6], states[..., -2:]], dim=-1)
         else:
-            input_states = torch.cat([states[..., :6], states[..., [-1]]], dim=-1)
+            input_states = torch.cat([states[..., :6], states[..., -1:]], dim=-1)
             input_states[..., 6:] = torch.div(input_states[..., 6:] + 1, 2, rounding_mode="floor")
         actions = batch["actions"].clone()
         actions[..., 6:] = torch.div(actions[..., 6:] + 1, 2, rounding_mode="floor")

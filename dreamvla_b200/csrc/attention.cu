@@ -10,6 +10,9 @@
 //   attn_bwd_dkv_kernel grid (ceil(Lk/64), H, B): per key tile, loops over query tiles, S^T/dP^T formulation
 //   attn_bwd_dq_kernel  grid (ceil(Lq/64), H, B): per query tile, loops over key tiles
 // Masking: tile_flags[qt, kt] in {0 skip, 1 partial, 2 full}; partial tiles test bits of mask[i, j/32].
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "../../include/dvla.h"
 
@@ -577,6 +580,18 @@ static bool strides_ok(const void* ptr, long long sb, long long ss, long long sh
   return ptr && (reinterpret_cast<uintptr_t>(ptr) % 16 == 0) && sb % 8 == 0 && ss % 8 == 0 && sh % 8 == 0;
 }
 
+int attn_fwd_tc_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s);   // attention_tc.cu (tcgen05 / TMEM)
+
+// 0 = auto (tcgen05 kernel for Lq >= 96, mma.sync kernel for short query blocks), 1 = force mma.sync, 2 = force tcgen05
+static int attn_fwd_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("DVLA_ATTN_FWD");
+    mode = (e && !strcmp(e, "legacy")) ? 1 : (e && !strcmp(e, "tc")) ? 2 : 0;
+  }
+  return mode;
+}
+
 int attn_fwd_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s) {
   if (!a) { set_error("attn_fwd: null args"); return DVLA_ERR_INVALID; }
   if (!strides_ok(a->q, a->q_sb, a->q_ss, a->q_sh) || !strides_ok(a->k, a->k_sb, a->k_ss, a->k_sh) ||
@@ -587,11 +602,16 @@ int attn_fwd_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s) {
   if (a->B <= 0 || a->H <= 0 || a->Lq <= 0 || a->Lk <= 0) { set_error("attn_fwd: non-positive dims"); return DVLA_ERR_INVALID; }
   if (a->H > 65535 || a->B > 65535) { set_error("attn_fwd: B,H must be <= 65535"); return DVLA_ERR_UNSUPPORTED; }
   if (a->mask && a->mask_words * 32 < a->Lk) { set_error("attn_fwd: mask_words too small"); return DVLA_ERR_INVALID; }
+  if (a->mask && !a->tile_flags) { set_error("attn_fwd: mask given without tile_flags"); return DVLA_ERR_INVALID; }
+  const int mode = attn_fwd_mode();
+  if (mode == 2 || (mode == 0 && a->Lq >= 96)) {
+    const int rc = attn_fwd_tc_dispatch(a, s);
+    if (rc != DVLA_ERR_UNSUPPORTED) return rc;      // strides a tensor map cannot express -> mma.sync kernel below
+  }
   AttnParams p;
   memset(&p, 0, sizeof(p));
   p.q = (const bf16*)a->q; p.k = (const bf16*)a->k; p.v = (const bf16*)a->v; p.out = (bf16*)a->o; p.lse = a->lse;
   p.mask = a->mask; p.tile_flags = a->mask ? a->tile_flags : nullptr;
-  if (a->mask && !a->tile_flags) { set_error("attn_fwd: mask given without tile_flags"); return DVLA_ERR_INVALID; }
   p.B = (int)a->B; p.H = (int)a->H; p.Lq = (int)a->Lq; p.Lk = (int)a->Lk;
   p.nqt = (p.Lq + 63) / 64; p.nkt = (p.Lk + 63) / 64; p.mask_words = a->mask_words;
   p.q_sb = a->q_sb; p.q_ss = a->q_ss; p.q_sh = a->q_sh; p.k_sb = a->k_sb; p.k_ss = a->k_ss; p.k_sh = a->k_sh;

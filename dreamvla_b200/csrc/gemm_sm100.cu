@@ -495,6 +495,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+EncodeTiledFn get_encode_fn_shared() { return get_encode_fn(); }
+
 // 2-D bf16 tensor map: inner dim contiguous, 128B swizzle, zero OOB fill.
 bool make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                        uint32_t box_inner, uint32_t box_outer) {

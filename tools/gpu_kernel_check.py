@@ -260,6 +260,9 @@ def attn_case(B, H, Lq, Lk, masked, fused_qkv=False, seed=3, timeit=False):
 
 
 def group_attn():
+    attn_case(1, 1, 128, 128, False)
+    attn_case(1, 2, 130, 257, False)
+    attn_case(2, 2, 300, 140, True)
     attn_case(1, 1, 64, 64, False)
     attn_case(2, 3, 197, 197, False, fused_qkv=True)
     attn_case(2, 2, 16, 212, False)

@@ -10,3 +10,8 @@ for g in ${CHECK_GROUPS:-gemm_basic gemm_epilogue gemm_big norm attn loss}; do
   grep -E "FAIL|GROUP|INFO|exit=|Error|error|watchdog" gpurun_out/check_$g.log | head -40
   grep -E "TFLOP|us" gpurun_out/check_$g.log | grep PASS | head -20
 done
+if [[ " ${CHECK_GROUPS:-attn} " == *" attn "* ]]; then
+  echo "=== attn (DVLA_ATTN_FWD=legacy)"
+  DVLA_ATTN_FWD=legacy timeout ${GROUP_TIMEOUT:-240} python tools/gpu_kernel_check.py attn > gpurun_out/check_attn_legacy.log 2>&1
+  grep -E "FAIL|GROUP|Error|watchdog" gpurun_out/check_attn_legacy.log | head -20
+fi

@@ -604,7 +604,7 @@ int attn_fwd_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s) {
   if (a->mask && a->mask_words * 32 < a->Lk) { set_error("attn_fwd: mask_words too small"); return DVLA_ERR_INVALID; }
   if (a->mask && !a->tile_flags) { set_error("attn_fwd: mask given without tile_flags"); return DVLA_ERR_INVALID; }
   const int mode = attn_fwd_mode();
-  if (mode == 2 || (mode == 0 && a->Lq >= 96)) {
+  if (mode == 2) {   // the tcgen05 forward is parity-green but not yet faster than the mma.sync kernel: opt-in
     const int rc = attn_fwd_tc_dispatch(a, s);
     if (rc != DVLA_ERR_UNSUPPORTED) return rc;      // strides a tensor map cannot express -> mma.sync kernel below
   }

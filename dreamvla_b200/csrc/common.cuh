@@ -113,6 +113,53 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// ---- cta_group::2 (CTA pair) variants --------------------------------------------------------------------------------
+// In a 2-CTA cluster the shared::cluster address of an object in CTA r is (cta-local address | r << 24); masking bit 24
+// addresses the leader (rank 0) copy.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// TMA load executed by either CTA of the pair into ITS OWN smem, completing tx bytes on the LEADER's mbarrier.
+__device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+// arrive on the LEADER CTA's copy of `bar` (callable from either CTA)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all prior MMAs of this thread completed) on `bar` in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+
 // TMEM -> registers: 32 lanes x 32 consecutive fp32 columns; thread t of the warp receives lane (base_lane + t).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -179,29 +226,48 @@ __device__ __forceinline__ float warp_max(float v) {
 // Activations (fp32 math).  Ids are part of the C ABI (include/dvla.h).
 enum Act : int { ACT_NONE = 0, ACT_GELU_ERF = 1, ACT_GELU_TANH = 2, ACT_QUICK_GELU = 3, ACT_RELU = 4, ACT_SILU = 5 };
 
-// erf with |abs error| <= 1.5e-7 (Abramowitz & Stegun 7.1.26): 5 FMA + rcp + exp -- the GEMM epilogue is ALU-bound for
-// K ~ 1024 with libdevice erff (~25 instructions per element).
+// Branch-free approximate reciprocal / exp2 (single MUFU each).  The IEEE variants (`/`, __frcp_rn, expf) compile to a MUFU
+// plus a guarded slow path -- one branch per element -- which made the GEMM epilogue instruction-bound (47 warp
+// instructions per output element in the first ncu capture, profiles/r1_gemm_epilogue_v1.txt).
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) {   // 1 / (1 + e^-x)
+  return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x));
+}
+// erf with |abs error| <= 1.5e-7 + MUFU approximation error (Abramowitz & Stegun 7.1.26): ~16 branch-free instructions.
 __device__ __forceinline__ float fast_erf(float x) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  const float r = 1.0f - p * t * __expf(-ax * ax);
+  const float e = ex2_approx(ax * ax * -1.4426950408889634f);
+  const float r = fmaf(-p * t, e, 1.0f);
   return copysignf(r, x);
 }
 
 __device__ __forceinline__ float act_fwd(float x, int act) {
   switch (act) {
-    case ACT_GELU_ERF: return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f));
-    case ACT_GELU_TANH: {  // 0.5x(1+tanh(u)) == x*sigmoid(2u)
-      float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-      return x / (1.0f + __expf(-2.0f * u));
+    case ACT_GELU_ERF: {
+      const float hx = 0.5f * x;
+      return fmaf(hx, fast_erf(x * 0.70710678118654752f), hx);
     }
-    case ACT_QUICK_GELU: return x / (1.0f + __expf(-1.702f * x));
+    case ACT_GELU_TANH: {  // 0.5x(1+tanh(u)) == x*sigmoid(2u)
+      const float u = x * fmaf(0.0356774081f, x * x, 0.7978845608028654f);   // sqrt(2/pi)(x + 0.044715x^3)
+      return x * sigmoid_fast(2.0f * u);
+    }
+    case ACT_QUICK_GELU: return x * sigmoid_fast(1.702f * x);
     case ACT_RELU: return fmaxf(x, 0.0f);
-    case ACT_SILU: return x / (1.0f + __expf(-x));
+    case ACT_SILU: return x * sigmoid_fast(x);
     default: return x;
   }
 }
@@ -237,25 +303,25 @@ __device__ __forceinline__ void act_fwd_n(float (&v)[N], int act) {
 __device__ __forceinline__ float act_bwd(float x, int act) {
   switch (act) {
     case ACT_GELU_ERF: {
-      float cdf = 0.5f * (1.0f + fast_erf(x * 0.70710678118654752f));
-      float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-      return cdf + x * pdf;
+      const float cdf = fmaf(0.5f, fast_erf(x * 0.70710678118654752f), 0.5f);
+      const float pdf = 0.3989422804014327f * ex2_approx(x * x * -0.7213475204444817f);   // exp(-x^2/2)/sqrt(2pi)
+      return fmaf(x, pdf, cdf);
     }
     case ACT_GELU_TANH: {
-      float x2 = x * x;
-      float u = 0.7978845608028654f * (x + 0.044715f * x * x2);
-      float s = 1.0f / (1.0f + __expf(-2.0f * u));  // sigmoid(2u)
-      float du = 0.7978845608028654f * (1.0f + 3.0f * 0.044715f * x2);
-      return s + x * s * (1.0f - s) * 2.0f * du;
+      const float x2 = x * x;
+      const float u = x * fmaf(0.0356774081f, x2, 0.7978845608028654f);
+      const float s = sigmoid_fast(2.0f * u);
+      const float du = fmaf(0.1070322243f, x2, 0.7978845608028654f);            // sqrt(2/pi)(1 + 3*0.044715 x^2)
+      return fmaf(x * s * (1.0f - s), 2.0f * du, s);
     }
     case ACT_QUICK_GELU: {
-      float s = 1.0f / (1.0f + __expf(-1.702f * x));
-      return s + 1.702f * x * s * (1.0f - s);
+      const float s = sigmoid_fast(1.702f * x);
+      return fmaf(1.702f * x * s, 1.0f - s, s);
     }
     case ACT_RELU: return x > 0.0f ? 1.0f : 0.0f;
     case ACT_SILU: {
-      float s = 1.0f / (1.0f + __expf(-x));
-      return s + x * s * (1.0f - s);
+      const float s = sigmoid_fast(x);
+      return fmaf(x * s, 1.0f - s, s);
     }
     default: return 1.0f;
   }

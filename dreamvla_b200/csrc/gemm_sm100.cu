@@ -440,10 +440,188 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-// ---- SIMT kernel of identical semantics for operands TMA cannot address (unaligned strides, K or N < 8) ------------
+
+// =====================================================================================================================
+// CTA-pair variant: tcgen05.mma.cta_group::2, 256 x 256 output tile per cluster of 2 CTAs.
+// Each CTA stages ITS 128 rows of A and ITS 128 rows (N-half) of B per k-block (32 KB/stage instead of 48 KB for the same
+// MMA work): L2->SM operand traffic per FLOP drops by a third, which is what bounds the single-CTA kernel on large GEMMs.
+// Leader CTA (rank 0) issues all MMAs; its `full` barriers collect the TMA bytes of both CTAs; tcgen05.commit multicasts
+// the stage-free / accumulator-ready arrivals to both CTAs; every epilogue warp of both CTAs arrives on the leader's
+// accumulator-free barrier.
+// =====================================================================================================================
+struct Gemm2Cfg {
+  static constexpr int BN = 256;
+  static constexpr int A_BYTES = BM * BK * 2;        // this CTA's 128 rows of A
+  static constexpr int B_BYTES = 128 * BK * 2;       // this CTA's 128 rows (N-half) of B
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 6;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int STAGING_BYTES = NUM_EPI_WARPS * 4096;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + BAR_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;
+};
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const GemmParams p) {
+  using Cfg = Gemm2Cfg;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
+  uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 2);            // leader's own arrive.expect_tx + the peer's remote arrive
+      mbar_init(&empty_bar[s], 1);           // multicast tcgen05.commit
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);           // multicast tcgen05.commit
+      mbar_init(&tempty_bar[s], 2 * NUM_EPI_WARPS);   // epilogue warps of both CTAs (used on the leader only)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2cta(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m2 = (p.M + 2 * BM - 1) / (2 * BM);
+  const int total_tiles = num_m2 * p.num_n_tiles;
+  const int num_clusters = gridDim.x >> 1;
+  const int cluster_id = blockIdx.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const int m0 = (tile % num_m2) * (2 * BM) + rank * BM;
+        const int n0 = (tile / num_m2) * BN + rank * 128;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
+          else        mbar_arrive_leader(&full_bar[s]);
+          uint8_t* a_dst = sA + s * Cfg::A_BYTES;
+          uint8_t* b_dst = sB + s * Cfg::B_BYTES;
+          if (!A_MN) {
+            tma_load_2d_2cta(a_dst, &tmA, &full_bar[s], kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) tma_load_2d_2cta(a_dst + i * (BK * 128), &tmA, &full_bar[s], m0 + i * 64, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d_2cta(b_dst, &tmB, &full_bar[s], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) tma_load_2d_2cta(b_dst + i * (BK * 128), &tmB, &full_bar[s], n0 + i * 64, kb * BK);
+          }
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, A_MN, B_MN);
+      int s = 0;
+      uint32_t ph = 0;
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + s * Cfg::A_BYTES);
+          const uint32_t b_base = smem_u32(sB + s * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t a_desc = A_MN ? make_smem_desc_sw128(a_base + k * (UMMA_K * 128), BK * 128, 1024)
+                                         : make_smem_desc_sw128(a_base + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t b_desc = B_MN ? make_smem_desc_sw128(b_base + k * (UMMA_K * 128), BK * 128, 1024)
+                                         : make_smem_desc_sw128(b_base + k * (UMMA_K * 2), 16, 1024);
+            umma_bf16_ss_2cta(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2cta(&empty_bar[s]);
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit_2cta(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_ph ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    uint8_t* stage = staging + (warp - 2) * 4096;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const int m0 = (tile % num_m2) * (2 * BM) + rank * BM;
+      const int n0 = (tile / num_m2) * BN;
+      mbar_wait(&tfull_bar[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      constexpr int PANELS = BN / 2 / 64;
+#pragma unroll 1
+      for (int pi = 0; pi < PANELS; ++pi) {
+        const int c = half * (BN / 2) + pi * 64;
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(t_lane + c, r0);
+        tmem_ld_32x32(t_lane + c + 32, r1);
+        tmem_ld_wait();
+        if (pi == PANELS - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+        }
+        if (n0 + c < p.N) {
+          float v[64];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
+          epilogue_panel_staged(v, stage, lane, m0 + q * 32, n0 + c, p);
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_ph ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ---- SIMT kernels of identical semantics for operands TMA cannot address (unaligned strides, K or N < 8) -------------
+// thread-per-(row, 8 columns) for short contractions; warp-per-(row, 8 columns) with a lane-strided k loop when the
+// contraction is long and the output small (wgrad of the 7-wide DiT layers: 5 k outputs x K = 960).
+__device__ __forceinline__ float simt_a(const bf16* a, long long lda, int a_mn, int row, int k) {
+  return __bfloat162float(a_mn ? a[static_cast<long long>(k) * lda + row] : a[static_cast<long long>(row) * lda + k]);
+}
+__device__ __forceinline__ float simt_b(const bf16* b, long long ldb, int b_mn, int n, int k) {
+  return __bfloat162float(b_mn ? b[static_cast<long long>(k) * ldb + n] : b[static_cast<long long>(n) * ldb + k]);
+}
 __global__ void gemm_simt_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, long long lda, long long ldb,
                                  int a_mn, int b_mn, GemmParams p) {
-  // one warp per output element group of 8 columns? keep it simple: one thread per (row, 8-col group), k loop.
   const long long groups_n = (p.N + 7) / 8;
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (gid >= static_cast<long long>(p.M) * groups_n) return;
@@ -454,17 +632,34 @@ __global__ void gemm_simt_kernel(const bf16* __restrict__ a, const bf16* __restr
   for (int j = 0; j < 8; ++j) v[j] = 0.f;
   const int nvalid = min(8, p.N - col);
   for (int k = 0; k < p.K; ++k) {
-    const float av = __bfloat162float(a_mn ? a[static_cast<long long>(k) * lda + row] : a[static_cast<long long>(row) * lda + k]);
+    const float av = simt_a(a, lda, a_mn, row, k);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (j < nvalid) {
-        const int n = col + j;
-        const float bv = __bfloat162float(b_mn ? b[static_cast<long long>(k) * ldb + n] : b[static_cast<long long>(n) * ldb + k]);
-        v[j] = fmaf(av, bv, v[j]);
-      }
-    }
+    for (int j = 0; j < 8; ++j)
+      if (j < nvalid) v[j] = fmaf(av, simt_b(b, ldb, b_mn, col + j, k), v[j]);
   }
   epilogue8(v, row, col, p);
+}
+__global__ void gemm_simt_warp_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, long long lda, long long ldb,
+                                      int a_mn, int b_mn, GemmParams p) {
+  const long long groups_n = (p.N + 7) / 8;
+  const long long wid = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= static_cast<long long>(p.M) * groups_n) return;      // warp-uniform
+  const int row = static_cast<int>(wid / groups_n);
+  const int col = static_cast<int>(wid % groups_n) * 8;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  const int nvalid = min(8, p.N - col);
+  for (int k = lane; k < p.K; k += 32) {
+    const float av = simt_a(a, lda, a_mn, row, k);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < nvalid) v[j] = fmaf(av, simt_b(b, ldb, b_mn, col + j, k), v[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = warp_sum(v[j]);
+  if (lane == 0) epilogue8(v, row, col, p);
 }
 
 }  // namespace dvla
@@ -472,6 +667,7 @@ __global__ void gemm_simt_kernel(const bf16* __restrict__ a, const bf16* __restr
 // ============================================== host side ========================================================
 #include <mutex>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace dvla {
@@ -542,6 +738,41 @@ static int launch_tc(const dvla_gemm_args* a, const GemmParams& p, cudaStream_t 
   return DVLA_OK;
 }
 
+template <bool A_MN, bool B_MN>
+static int launch_tc2(const dvla_gemm_args* a, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg;
+  CUtensorMap tmA, tmB;
+  if (!A_MN) { if (!make_tmap_2d_bf16(&tmA, a->a, a->K, a->M, a->lda, BK, BM)) return DVLA_ERR_CUDA; }
+  else       { if (!make_tmap_2d_bf16(&tmA, a->a, a->M, a->K, a->lda, 64, BK)) return DVLA_ERR_CUDA; }
+  if (!B_MN) { if (!make_tmap_2d_bf16(&tmB, a->b, a->K, a->N, a->ldb, BK, 128)) return DVLA_ERR_CUDA; }
+  else       { if (!make_tmap_2d_bf16(&tmB, a->b, a->N, a->K, a->ldb, 64, BK)) return DVLA_ERR_CUDA; }
+  auto kern = gemm_tcgen05_2cta_kernel<A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(2cta smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return DVLA_ERR_CUDA; }
+    attr_set = true;
+  }
+  const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * p.num_n_tiles;
+  const int max_clusters = num_sms() / 2;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  kern<<<2 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("gemm_tcgen05_2cta launch: %s", cudaGetErrorString(e)); return DVLA_ERR_CUDA; }
+  count_launch();
+  return DVLA_OK;
+}
+
+// 0 = auto, 1 = force single-CTA kernels, 2 = force the CTA-pair kernel whenever legal
+static int gemm_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("DVLA_GEMM");
+    mode = (e && !strcmp(e, "1cta")) ? 1 : (e && !strcmp(e, "2cta")) ? 2 : 0;
+  }
+  return mode;
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 int gemm_dispatch(const dvla_gemm_args* a, cudaStream_t stream) {
@@ -576,16 +807,40 @@ int gemm_dispatch(const dvla_gemm_args* a, cudaStream_t stream) {
   if (!tma_ok) {
     const long long groups = (long long)p.M * ((p.N + 7) / 8);
     const int threads = 128;
-    const long long blocks = (groups + threads - 1) / threads;
-    gemm_simt_kernel<<<(unsigned)blocks, threads, 0, stream>>>((const bf16*)a->a, (const bf16*)a->b, a->lda, a->ldb,
-                                                             a->a_mn_major, a->b_mn_major, p);
+    if (p.K >= 128 && groups <= 65536) {      // long contraction, small output: one warp per output group
+      const long long blocks = (groups * 32 + threads - 1) / threads;
+      gemm_simt_warp_kernel<<<(unsigned)blocks, threads, 0, stream>>>((const bf16*)a->a, (const bf16*)a->b, a->lda, a->ldb,
+                                                                    a->a_mn_major, a->b_mn_major, p);
+    } else {
+      const long long blocks = (groups + threads - 1) / threads;
+      gemm_simt_kernel<<<(unsigned)blocks, threads, 0, stream>>>((const bf16*)a->a, (const bf16*)a->b, a->lda, a->ldb,
+                                                               a->a_mn_major, a->b_mn_major, p);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("gemm_simt launch: %s", cudaGetErrorString(e)); return DVLA_ERR_CUDA; }
     count_launch();
     return DVLA_OK;
   }
-  // tile-width heuristic: fewer, fatter tiles unless that leaves SMs idle for a whole extra wave
   const int sms = num_sms();
+  // CTA-pair kernel (256x256 tiles, staged bf16 epilogue): when the problem fills the 74 SM pairs at least as well as
+  // the single-CTA tiling fills the 148 SMs
+  if (p.staged_ok && gemm_mode() != 1) {
+    const long long t2 = (long long)((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + 255) / 256);
+    const long long t1 = (long long)p.num_m_tiles * ((p.N + 255) / 256);
+    const long long r2 = (t2 + sms / 2 - 1) / (sms / 2), r1 = (t1 + sms - 1) / sms;
+    const bool big = (long long)p.M * p.N >= 256LL * 256 * 40;
+    if (gemm_mode() == 2 || (big && p.N > 128 && r2 <= r1)) {
+      p.num_n_tiles = (p.N + 255) / 256;
+      const int key2 = (a->a_mn_major ? 2 : 0) | (a->b_mn_major ? 1 : 0);
+      switch (key2) {
+        case 0: return launch_tc2<false, false>(a, p, stream);
+        case 1: return launch_tc2<false, true>(a, p, stream);
+        case 2: return launch_tc2<true, false>(a, p, stream);
+        default: return launch_tc2<true, true>(a, p, stream);
+      }
+    }
+  }
+  // tile-width heuristic: fewer, fatter tiles unless that leaves SMs idle for a whole extra wave
   const long long t128 = (long long)p.num_m_tiles * ((p.N + 127) / 128);
   const long long t256 = (long long)p.num_m_tiles * ((p.N + 255) / 256);
   const long long cost128 = (t128 + sms - 1) / sms;

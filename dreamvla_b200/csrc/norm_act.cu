@@ -201,7 +201,7 @@ int layernorm_bwd_dispatch(const dvla_layernorm_bwd_args* a, cudaStream_t stream
   if (a->rows <= 0) return DVLA_OK;
   const int nv = (int)((a->D + 255) / 256);
   long long blocks = (a->rows + 7) / 8;
-  const long long cap = (long long)num_sms() * 2;
+  const long long cap = (long long)num_sms();   // fewer, longer-lived blocks: 2*D fp32 atomics per block at the end
   if (blocks > cap) blocks = cap;
 #define LN_BWD(NV) layernorm_bwd_kernel<NV><<<(unsigned)blocks, 256, 0, stream>>>((const bf16*)a->dy, (const bf16*)a->x, \
       (const bf16*)a->gamma, a->mean, a->rstd, (bf16*)a->dx, a->dgamma, a->dbeta, a->rows, (int)a->D, a->ld)
@@ -213,43 +213,55 @@ int layernorm_bwd_dispatch(const dvla_layernorm_bwd_args* a, cudaStream_t stream
 
 // ------------------------------------------------------------------------------------------------------------------
 // Column sum (bias gradient): out[n] += sum_r x[r, n]
+// Block = 8 warps over a slab of 256 columns x a chunk of rows: each lane keeps 8 column partials in registers (coalesced
+// 512 B per warp per row), the 8 warps fold through shared memory, ONE fp32 atomicAdd per column per block.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) colsum_kernel(const bf16* __restrict__ x, long long rows, int N, long long ld,
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, long long rows, int N, long long ld,
                                                      float* __restrict__ out, int rows_per_block, int vec) {
   const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
   const long long r1 = min(rows, r0 + rows_per_block);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ float red[8][257];
   if (vec) {
-    const int cg = blockIdx.x * blockDim.x + threadIdx.x;  // 8-column group
-    if (cg * 8 >= N) return;
+    const int col = blockIdx.x * 256 + lane * 8;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (long long r = r0; r < r1; ++r) {
-      float f[8];
-      load8(x + r * ld + cg * 8, f);
+    if (col < N) {
+      for (long long r = r0 + warp; r < r1; r += 8) {
+        float f[8];
+        load8(x + r * ld + col, f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(out + cg * 8 + j, acc[j]);
+    for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
   } else {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= N) return;
+    const int col = blockIdx.x * 256 + threadIdx.x;   // scalar path: thread per column, all rows of the chunk
     float acc = 0.f;
-    for (long long r = r0; r < r1; ++r) acc += __bfloat162float(x[r * ld + c]);
-    atomicAdd(out + c, acc);
+    if (col < N)
+      for (long long r = r0; r < r1; ++r) acc += __bfloat162float(x[r * ld + col]);
+    if (col < N) atomicAdd(out + col, acc);
+    return;
   }
+  __syncthreads();
+  const int c = threadIdx.x;
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += red[w][c];
+  const int col = blockIdx.x * 256 + c;
+  if (col < N) atomicAdd(out + col, t);
 }
 int colsum_accum_dispatch(const void* x, int64_t rows, int64_t N, int64_t ld, float* out, cudaStream_t s) {
   if (!x || !out) { set_error("colsum: null pointer"); return DVLA_ERR_INVALID; }
   if (rows <= 0 || N <= 0) return DVLA_OK;
   const int vec = (N % 8 == 0) && (ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  const long long cols = vec ? N / 8 : N;
-  const int bx = (int)((cols + 127) / 128);
+  const int bx = (int)((N + 255) / 256);
   int by = (int)((2LL * num_sms() + bx - 1) / bx);
-  if (by > rows) by = (int)rows;
+  if (by > (rows + 31) / 32) by = (int)((rows + 31) / 32);
   if (by < 1) by = 1;
   const int rpb = (int)((rows + by - 1) / by);
   by = (int)((rows + rpb - 1) / rpb);
-  colsum_kernel<<<dim3(bx, by), 128, 0, s>>>((const bf16*)x, rows, (int)N, ld, out, rpb, vec);
+  colsum_kernel<<<dim3(bx, by), 256, 0, s>>>((const bf16*)x, rows, (int)N, ld, out, rpb, vec);
   DVLA_CHECK_LAUNCH("colsum");
   return DVLA_OK;
 }

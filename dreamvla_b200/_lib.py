@@ -54,7 +54,8 @@ class AttnBwdArgs(C.Structure):
                 ("do_sb", _i64), ("do_ss", _i64), ("do_sh", _i64),
                 ("dq_sb", _i64), ("dq_ss", _i64), ("dq_sh", _i64), ("dk_sb", _i64), ("dk_ss", _i64), ("dk_sh", _i64),
                 ("dv_sb", _i64), ("dv_ss", _i64), ("dv_sh", _i64),
-                ("mask_words", _i32), ("scale", _f32), ("dropout_p", _f32), ("dropout_seed", _u64), ("dropout_seed_ptr", _vp)]
+                ("mask_words", _i32), ("scale", _f32), ("dropout_p", _f32), ("dropout_seed", _u64), ("dropout_seed_ptr", _vp),
+                ("mask_t", _vp), ("mask_t_words", _i32)]
 
 
 class AdamWArgs(C.Structure):
@@ -208,7 +209,7 @@ def attn_fwd(q, k, v, scale, mask_bits=None, tile_flags=None, dropout_p=0.0, dro
 
 
 def attn_bwd(q, k, v, o, d_o, lse, scale, dq, dk, dv, mask_bits=None, tile_flags=None, dropout_p=0.0, dropout_seed=0,
-             dropout_seed_ptr=None):
+             dropout_seed_ptr=None, mask_bits_t=None):
     B, Lq, H, _ = q.shape
     Lk = k.shape[1]
     delta = torch.empty((B, H, Lq), device=q.device, dtype=torch.float32)
@@ -229,6 +230,8 @@ def attn_bwd(q, k, v, o, d_o, lse, scale, dq, dk, dv, mask_bits=None, tile_flags
     a.mask_words = 0 if mask_bits is None else mask_bits.shape[1]
     a.scale, a.dropout_p, a.dropout_seed = float(scale), float(dropout_p), int(dropout_seed)
     a.dropout_seed_ptr = _ptr(dropout_seed_ptr)
+    a.mask_t = _ptr(mask_bits_t)
+    a.mask_t_words = 0 if mask_bits_t is None else mask_bits_t.shape[1]
     _check(load().dvla_attn_bwd(C.byref(a), _stream()), "dvla_attn_bwd")
 
 

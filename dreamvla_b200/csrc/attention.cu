@@ -628,6 +628,18 @@ int attn_fwd_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s) {
   return DVLA_OK;
 }
 
+int attn_bwd_tc_dispatch(const dvla_attn_bwd_args* a, const uint32_t* mask_t, int mask_t_words, cudaStream_t s);  // attention_bwd_tc.cu
+
+// 0 = auto (tcgen05 kernels when both sequences are >= 96 long), 1 = force mma.sync, 2 = force tcgen05
+static int attn_bwd_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("DVLA_ATTN_BWD");
+    mode = (e && !strcmp(e, "legacy")) ? 1 : (e && !strcmp(e, "tc")) ? 2 : 0;
+  }
+  return mode;
+}
+
 int attn_bwd_dispatch(const dvla_attn_bwd_args* a, cudaStream_t s) {
   if (!a) { set_error("attn_bwd: null args"); return DVLA_ERR_INVALID; }
   if (!strides_ok(a->q, a->q_sb, a->q_ss, a->q_sh) || !strides_ok(a->k, a->k_sb, a->k_ss, a->k_sh) ||
@@ -663,6 +675,11 @@ int attn_bwd_dispatch(const dvla_attn_bwd_args* a, cudaStream_t s) {
   const long long rows = (long long)p.B * p.H * p.Lq;
   attn_delta_kernel<<<(unsigned)((rows * 8 + 255) / 256), 256, 0, s>>>(p);
   DVLA_CHECK_LAUNCH("attn_delta");
+  const int bmode = attn_bwd_mode();
+  if (bmode == 2 || (bmode == 0 && a->Lq >= 96 && a->Lk >= 96)) {
+    const int rc = attn_bwd_tc_dispatch(a, a->mask_t, a->mask_t_words, s);
+    if (rc != DVLA_ERR_UNSUPPORTED) return rc;
+  }
   attn_bwd_dkv_kernel<<<dim3(p.nkt, p.H, p.B), 128, 0, s>>>(p);
   DVLA_CHECK_LAUNCH("attn_bwd_dkv");
   attn_bwd_dq_kernel<<<dim3(p.nqt, p.H, p.B), 128, 0, s>>>(p);

@@ -187,6 +187,7 @@ class AttnMask:
     def __init__(self, visible_bool: torch.Tensor, device):
         self.Lq, self.Lk = visible_bool.shape
         self.bits = self.pack_bits(visible_bool).to(device).contiguous()
+        self.bits_t = self.pack_bits(visible_bool.t().contiguous()).to(device).contiguous()   # [Lk, ceil(Lq/32)]
         self.flags = L.attn_mask_tiles(self.bits, self.Lq, self.Lk)
 
     @staticmethod
@@ -231,7 +232,8 @@ class _Attention(torch.autograd.Function):
             dv = torch.empty(v.shape, device=v.device, dtype=torch.bfloat16)
         L.attn_bwd(q, k, v, o, d_o, lse, scale, dq, dk, dv, mask.bits if mask is not None else None,
                    mask.flags if mask is not None else None, dropout_p, seed,
-                   dropout_seed_ptr=seed_counter(q.device) if dropout_p > 0 else None)
+                   dropout_seed_ptr=seed_counter(q.device) if dropout_p > 0 else None,
+                   mask_bits_t=mask.bits_t if mask is not None else None)
         return dq, dk, dv, None, None, None
 
 
@@ -264,7 +266,8 @@ class _FusedQKVAttention(torch.autograd.Function):
         dqkv = torch.empty_like(qkv)
         L.attn_bwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], o, d_o, lse, scale, dqkv[:, :, 0], dqkv[:, :, 1],
                    dqkv[:, :, 2], mask.bits if mask is not None else None, mask.flags if mask is not None else None,
-                   dropout_p, seed, dropout_seed_ptr=seed_counter(qkv.device) if dropout_p > 0 else None)
+                   dropout_p, seed, dropout_seed_ptr=seed_counter(qkv.device) if dropout_p > 0 else None,
+                   mask_bits_t=mask.bits_t if mask is not None else None)
         return dqkv, None, None, None
 
 

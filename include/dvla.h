@@ -141,6 +141,9 @@ typedef struct {
   float scale;
   float dropout_p; uint64_t dropout_seed;
   const uint64_t* dropout_seed_ptr;
+  const uint32_t* mask_t;     /* optional TRANSPOSED bit matrix [Lk, mask_t_words] (bit i%32 of word i/32 of row j = pair (i,j)
+                                 visible); lets the tcgen05 dK/dV kernel read a key row's query bits contiguously */
+  int32_t mask_t_words;
 } dvla_attn_bwd_args;
 int dvla_attn_bwd(const dvla_attn_bwd_args* args, void* stream);
 

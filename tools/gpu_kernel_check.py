@@ -223,7 +223,7 @@ def attn_case(B, H, Lq, Lk, masked, fused_qkv=False, seed=3, timeit=False):
         q = torch.randn(B, Lq, H, 64, generator=g).to(dev, torch.bfloat16)
         k = torch.randn(B, Lk, H, 64, generator=g).to(dev, torch.bfloat16)
         v = torch.randn(B, Lk, H, 64, generator=g).to(dev, torch.bfloat16)
-    mask_bool = bits = flags = None
+    mask_bool = bits = flags = bits_t = None
     if masked:
         mask_bool = torch.rand(Lq, Lk, generator=g) < 0.3
         mask_bool[:, 0] = True                       # no fully-masked rows
@@ -231,6 +231,7 @@ def attn_case(B, H, Lq, Lk, masked, fused_qkv=False, seed=3, timeit=False):
             mask_bool[: Lq // 2, 64:128] = False     # a fully masked tile
             mask_bool[Lq // 2:, 64:128] = True       # a fully visible one (if Lq//2 is tile aligned)
         bits = pack_mask(mask_bool)
+        bits_t = pack_mask(mask_bool.t().contiguous())
         flags = L.attn_mask_tiles(bits, Lq, Lk)
         mask_bool = mask_bool.to(dev)
     scale = 0.125
@@ -249,10 +250,10 @@ def attn_case(B, H, Lq, Lk, masked, fused_qkv=False, seed=3, timeit=False):
         dq, dk, dv = dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2]
     else:
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-    L.attn_bwd(q, k, v, o, d_o, lse, scale, dq, dk, dv, bits, flags)
+    L.attn_bwd(q, k, v, o, d_o, lse, scale, dq, dk, dv, bits, flags, mask_bits_t=bits_t)
     oref.backward(d_o.float())
     if timeit:
-        ms = bench(lambda: L.attn_bwd(q, k, v, o, d_o, lse, scale, dq, dk, dv, bits, flags))
+        ms = bench(lambda: L.attn_bwd(q, k, v, o, d_o, lse, scale, dq, dk, dv, bits, flags, mask_bits_t=bits_t))
         extra = f"bwd {ms*1e3:.1f}us"
     report(tag + " dq", rel(dq, qr.grad), 1e-2, extra)
     report(tag + " dk", rel(dk, kr.grad), 1e-2)

@@ -11,7 +11,10 @@ for g in ${CHECK_GROUPS:-gemm_basic gemm_epilogue gemm_big norm attn loss}; do
   grep -E "TFLOP|us" gpurun_out/check_$g.log | grep PASS | head -20
 done
 if [[ " ${CHECK_GROUPS:-attn} " == *" attn "* ]]; then
-  echo "=== attn (DVLA_ATTN_FWD=legacy)"
-  DVLA_ATTN_FWD=legacy timeout ${GROUP_TIMEOUT:-240} python tools/gpu_kernel_check.py attn > gpurun_out/check_attn_legacy.log 2>&1
-  grep -E "FAIL|GROUP|Error|watchdog" gpurun_out/check_attn_legacy.log | head -20
+  for cfg in "DVLA_ATTN_FWD=legacy DVLA_ATTN_BWD=legacy" "DVLA_ATTN_FWD=tc DVLA_ATTN_BWD=tc"; do
+    echo "=== attn ($cfg)"
+    env $cfg timeout ${GROUP_TIMEOUT:-240} python tools/gpu_kernel_check.py attn > "gpurun_out/check_attn_${cfg// /_}.log" 2>&1
+    grep -E "FAIL|GROUP|Error|watchdog" "gpurun_out/check_attn_${cfg// /_}.log" | head -20
+    grep -E "us" "gpurun_out/check_attn_${cfg// /_}.log" | grep -E "fwd|dq" | cut -c1-120
+  done
 fi

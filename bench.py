@@ -223,7 +223,7 @@ def run_ours(args):
             N = b.shape[1] if b_mn else b.shape[0]
             tma = a.stride(0) % 8 == 0 and b.stride(0) % 8 == 0
             calls[(M, N, K, a_mn, b_mn, kw.get("bias") is not None, int(kw.get("act", 0)), kw.get("residual") is not None,
-                   kw.get("aux_out") is not None, float(kw.get("dropout_p", 0.0)) > 0, tma)] += 1
+                   kw.get("aux_out") is not None, float(kw.get("dropout_p", 0.0)) > 0, tma, kw.get("aux_in") is not None)] += 1
             return orig(a, b, **kw)
         _lib.gemm = rec_gemm
         try:
@@ -234,7 +234,7 @@ def run_ours(args):
         eager_step.flat.G.zero_()
         fl = tm = 0.0
         n_tc = 0
-        for (M, N, K, a_mn, b_mn, hb, act, hr, ha, hd, tma), cnt in calls.items():
+        for (M, N, K, a_mn, b_mn, hb, act, hr, ha, hd, tma, hai), cnt in calls.items():
             if not tma:
                 continue
             A = torch.randn((K, M) if a_mn else (M, K), device=dev, dtype=torch.bfloat16)
@@ -242,6 +242,7 @@ def run_ours(args):
             kw = dict(a_mn=a_mn, b_mn=b_mn, act=act, bias=torch.zeros(N, device=dev, dtype=torch.bfloat16) if hb else None,
                       residual=torch.zeros(M, N, device=dev, dtype=torch.bfloat16) if hr else None,
                       aux_out=torch.empty(M, N, device=dev, dtype=torch.bfloat16) if ha else None,
+                      aux_in=torch.zeros(M, N, device=dev, dtype=torch.bfloat16) if hai else None,
                       out=torch.empty(M, N, device=dev, dtype=torch.bfloat16), dropout_p=0.1 if hd else 0.0, dropout_seed=1)
             for _ in range(2):
                 orig(A, Bm, **kw)

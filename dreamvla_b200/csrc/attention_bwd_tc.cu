@@ -71,7 +71,8 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
 
 // ============================================================ dK / dV ==============================================================
 constexpr int KV_SM_K = 0, KV_SM_V = 16384, KV_SM_Q = 32768, KV_SM_DO = KV_SM_Q + 2 * 8192, KV_SM_P = KV_SM_DO + 2 * 8192,
-              KV_SM_DS = KV_SM_P + 16384, KV_SM_LSE = KV_SM_DS + 16384, KV_SM_BAR = KV_SM_LSE + 2 * 2 * 64 * 4;
+              KV_SM_DS = KV_SM_P + 16384, KV_SM_LSE = KV_SM_DS + 16384, KV_SM_FLAGS = KV_SM_LSE + 2 * 2 * 64 * 4,
+              KV_SM_BAR = KV_SM_FLAGS + 512;
 constexpr int ATTN_DKV_SMEM = KV_SM_BAR + 128 + 1024;
 
 __global__ void __launch_bounds__(128, 2)
@@ -108,21 +109,28 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
   const uint32_t tS = tmem_base, tDP = tmem_base + 64, tDV = tmem_base + 128, tDK = tmem_base + 192;
 
-  auto tile_flag = [&](int qt) -> int {      // (64-query tile qt) x (this 128-key tile)
-    if (!p.tile_flags) return 2;
-    int any = 0, all = 1;
+  // per-(64-query tile) flag of this 128-key tile, computed once into smem: 0 skip, 1 partial, 2 full
+  uint8_t* s_flags = smem + KV_SM_FLAGS;
+  for (int qi = tid; qi < nqt && qi < 512; qi += 128) {
+    int f = 2;
+    if (p.tile_flags) {
+      int any = 0, all = 1;
 #pragma unroll
-    for (int dk = 0; dk < 2; ++dk) {
-      const int k64 = kt * 2 + dk;
-      if (k64 * 64 >= p.Lk) continue;
-      const int f = p.tile_flags[static_cast<long long>(qt) * p.nkt64 + k64];
-      any |= (f != 0);
-      all &= (f == 2);
+      for (int dk = 0; dk < 2; ++dk) {
+        const int k64 = kt * 2 + dk;
+        if (k64 * 64 >= p.Lk) continue;
+        const int ff = p.tile_flags[static_cast<long long>(qi) * p.nkt64 + k64];
+        any |= (ff != 0);
+        all &= (ff == 2);
+      }
+      f = any ? (all ? 2 : 1) : 0;
     }
-    return any ? (all ? 2 : 1) : 0;
-  };
+    s_flags[qi] = static_cast<uint8_t>(f);
+  }
+  __syncthreads();
+  auto tile_flag = [&](int qt) -> int { return s_flags[qt]; };
   auto next_tile = [&](int qt) {
-    while (qt < nqt && tile_flag(qt) == 0) ++qt;
+    while (qt < nqt && s_flags[qt] == 0) ++qt;
     return qt;
   };
   auto load_q = [&](int qt, int st) {        // thread 0: Q and dO tiles of 64 rows -> stage st
@@ -145,20 +153,40 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);    // A = P^T/dS^T K-major, B = dO/Q MN-major
 
   int st = 0;
-  uint32_t ph_q[2] = {0, 0}, ph_s = 0, ph_o = 0;
+  uint32_t ph_q0 = 0, ph_q1 = 0, ph_s = 0, ph_o = 0;
   bool first = true, any_iter = false;
+  // software prefetch of the per-tile scalars (lse, delta for tid < 64; transposed mask words for every key row): the
+  // global loads of tile j+1 are issued at the top of iteration j and consumed at the top of iteration j+1
+  float pf_lse = INFINITY, pf_delta = 0.f;
+  uint32_t pf_w0 = 0xffffffffu, pf_w1 = 0xffffffffu;
+  auto prefetch = [&](int qtile) {
+    if (tid < 64) {
+      const int qi = qtile * 64 + tid;
+      pf_lse = (qi < p.Lq) ? p.lse[bh * p.Lq + qi] * B_LOG2E : INFINITY;
+      pf_delta = (qi < p.Lq) ? p.delta[bh * p.Lq + qi] : 0.f;
+    }
+    pf_w0 = pf_w1 = 0xffffffffu;
+    if (s_flags[qtile] == 1) {
+      const int wi = qtile * 2;
+      pf_w0 = (key < p.Lk && wi < p.mask_t_words) ? p.mask_t[static_cast<long long>(key) * p.mask_t_words + wi] : 0u;
+      pf_w1 = (key < p.Lk && wi + 1 < p.mask_t_words) ? p.mask_t[static_cast<long long>(key) * p.mask_t_words + wi + 1] : 0u;
+    }
+    if (key >= p.Lk) { pf_w0 = 0u; pf_w1 = 0u; }
+  };
+  if (qt < nqt) prefetch(qt);
   while (qt < nqt) {
     const int qt_next = next_tile(qt + 1);
     const int q0 = qt * 64;
     if (tid < 64) {                                  // per-query scalars of this tile -> smem (read by every key row)
-      const int qi = q0 + tid;
-      s_lse[st * 64 + tid] = (qi < p.Lq) ? p.lse[bh * p.Lq + qi] * B_LOG2E : INFINITY;
-      s_delta[st * 64 + tid] = (qi < p.Lq) ? p.delta[bh * p.Lq + qi] : 0.f;
+      s_lse[st * 64 + tid] = pf_lse;
+      s_delta[st * 64 + tid] = pf_delta;
     }
+    const uint32_t w0 = pf_w0, w1 = pf_w1;
+    if (qt_next < nqt) prefetch(qt_next);
     if (tid == 0) {
       if (qt_next < nqt) load_q(qt_next, st ^ 1);
       if (first) mbar_wait(bar_kv, 0);
-      mbar_wait(&bar_q[st], ph_q[st]);
+      mbar_wait(&bar_q[st], st ? ph_q1 : ph_q0);
       tc_fence_after();
       const uint32_t ka = smem_u32(smem + KV_SM_K), va = smem_u32(smem + KV_SM_V);
       const uint32_t qa = smem_u32(smem + KV_SM_Q + st * 8192), da = smem_u32(smem + KV_SM_DO + st * 8192);
@@ -170,22 +198,14 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         umma_bf16_ss(tDP, make_smem_desc_sw128(va + k * 32, 16, 1024), make_smem_desc_sw128(da + k * 32, 16, 1024), idesc_s, k != 0);
       umma_commit(bar_s);
     }
-    ph_q[st] ^= 1;
+    if (st) ph_q1 ^= 1; else ph_q0 ^= 1;
     first = false;
     __syncthreads();                                 // s_lse / s_delta visible
     mbar_wait(bar_s, ph_s);
     ph_s ^= 1;
     tc_fence_after();
 
-    // visibility of (query c, this key) for the 64 queries of the tile: two words of the transposed bit matrix
-    const int flag = tile_flag(qt);
-    uint32_t w0 = 0xffffffffu, w1 = 0xffffffffu;
-    if (flag == 1) {
-      const int wi = qt * 2;
-      w0 = (key < p.Lk && wi < p.mask_t_words) ? p.mask_t[static_cast<long long>(key) * p.mask_t_words + wi] : 0u;
-      w1 = (key < p.Lk && wi + 1 < p.mask_t_words) ? p.mask_t[static_cast<long long>(key) * p.mask_t_words + wi + 1] : 0u;
-    }
-    if (key >= p.Lk) { w0 = 0u; w1 = 0u; }
+    // visibility of (query c, this key) for the 64 queries of the tile: w0 / w1 = two words of the transposed bit matrix
     float sv[64], dpv[64];
     tmem_ld64(tS + lane_off, sv);
     tmem_ld64(tDP + lane_off, dpv);
@@ -259,7 +279,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
 // ============================================================== dQ =================================================================
 constexpr int DQ_SM_Q = 0, DQ_SM_DO = 16384, DQ_SM_K = 32768, DQ_SM_V = DQ_SM_K + 2 * 8192, DQ_SM_DS = DQ_SM_V + 2 * 8192,
-              DQ_SM_BAR = DQ_SM_DS + 16384;
+              DQ_SM_FLAGS = DQ_SM_DS + 16384, DQ_SM_BAR = DQ_SM_FLAGS + 512;
 constexpr int ATTN_DQ_SMEM = DQ_SM_BAR + 128 + 1024;
 
 __global__ void __launch_bounds__(128, 2)
@@ -294,21 +314,26 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
   const uint32_t tS = tmem_base, tDP = tmem_base + 64, tDQ = tmem_base + 128;
 
-  auto tile_flag = [&](int kt) -> int {      // (this 128-query tile) x (64-key tile kt)
-    if (!p.tile_flags) return 2;
-    int any = 0, all = 1;
+  uint8_t* s_flags = smem + DQ_SM_FLAGS;       // per-(64-key tile) flag of this 128-query tile
+  for (int ki = tid; ki < nkt && ki < 512; ki += 128) {
+    int f = 2;
+    if (p.tile_flags) {
+      int any = 0, all = 1;
 #pragma unroll
-    for (int dq = 0; dq < 2; ++dq) {
-      const int q64 = qt * 2 + dq;
-      if (q64 * 64 >= p.Lq) continue;
-      const int f = p.tile_flags[static_cast<long long>(q64) * p.nkt64 + kt];
-      any |= (f != 0);
-      all &= (f == 2);
+      for (int dq = 0; dq < 2; ++dq) {
+        const int q64 = qt * 2 + dq;
+        if (q64 * 64 >= p.Lq) continue;
+        const int ff = p.tile_flags[static_cast<long long>(q64) * p.nkt64 + ki];
+        any |= (ff != 0);
+        all &= (ff == 2);
+      }
+      f = any ? (all ? 2 : 1) : 0;
     }
-    return any ? (all ? 2 : 1) : 0;
-  };
+    s_flags[ki] = static_cast<uint8_t>(f);
+  }
+  __syncthreads();
   auto next_tile = [&](int kt) {
-    while (kt < nkt && tile_flag(kt) == 0) ++kt;
+    while (kt < nkt && s_flags[kt] == 0) ++kt;
     return kt;
   };
   auto load_kv = [&](int kt, int st) {
@@ -333,15 +358,27 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
 
   int st = 0;
-  uint32_t ph_kv[2] = {0, 0}, ph_s = 0, ph_o = 0;
+  uint32_t ph_kv0 = 0, ph_kv1 = 0, ph_s = 0, ph_o = 0;
   bool first = true, any_iter = false;
+  uint32_t pf_w0 = 0xffffffffu, pf_w1 = 0xffffffffu;     // mask words of the NEXT tile (software prefetch)
+  auto prefetch = [&](int ktile) {
+    pf_w0 = pf_w1 = 0xffffffffu;
+    if (s_flags[ktile] == 1) {
+      const int wi = ktile * 2;
+      pf_w0 = (row < p.Lq && wi < p.mask_words) ? p.mask[static_cast<long long>(row) * p.mask_words + wi] : 0u;
+      pf_w1 = (row < p.Lq && wi + 1 < p.mask_words) ? p.mask[static_cast<long long>(row) * p.mask_words + wi + 1] : 0u;
+    }
+  };
+  if (kt < nkt) prefetch(kt);
   while (kt < nkt) {
     const int kt_next = next_tile(kt + 1);
     const int k0 = kt * 64;
+    uint32_t w0 = pf_w0, w1 = pf_w1;
+    if (kt_next < nkt) prefetch(kt_next);
     if (tid == 0) {
       if (kt_next < nkt) load_kv(kt_next, st ^ 1);
       if (first) mbar_wait(bar_q, 0);
-      mbar_wait(&bar_kv[st], ph_kv[st]);
+      mbar_wait(&bar_kv[st], st ? ph_kv1 : ph_kv0);
       tc_fence_after();
       const uint32_t qa = smem_u32(smem + DQ_SM_Q), da = smem_u32(smem + DQ_SM_DO);
       const uint32_t ka = smem_u32(smem + DQ_SM_K + st * 8192), va = smem_u32(smem + DQ_SM_V + st * 8192);
@@ -353,19 +390,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         umma_bf16_ss(tDP, make_smem_desc_sw128(da + k * 32, 16, 1024), make_smem_desc_sw128(va + k * 32, 16, 1024), idesc_s, k != 0);
       umma_commit(bar_s);
     }
-    ph_kv[st] ^= 1;
+    if (st) ph_kv1 ^= 1; else ph_kv0 ^= 1;
     first = false;
     mbar_wait(bar_s, ph_s);
     ph_s ^= 1;
     tc_fence_after();
 
-    const int flag = tile_flag(kt);
-    uint32_t w0 = 0xffffffffu, w1 = 0xffffffffu;
-    if (flag == 1) {
-      const int wi = kt * 2;
-      w0 = (row < p.Lq && wi < p.mask_words) ? p.mask[static_cast<long long>(row) * p.mask_words + wi] : 0u;
-      w1 = (row < p.Lq && wi + 1 < p.mask_words) ? p.mask[static_cast<long long>(row) * p.mask_words + wi + 1] : 0u;
-    }
     if (k0 + 64 > p.Lk) {
       const int n0 = p.Lk - k0;                      // valid keys in this tile (1..63)
       w0 &= (n0 >= 32) ? 0xffffffffu : ((1u << n0) - 1u);

@@ -76,8 +76,8 @@ class GPT2MLP(nn.Module):
         self.resid_pdrop = config.resid_pdrop
 
     def forward(self, hidden_states, residual):
-        h = self.c_fc(hidden_states, act=self.act)
-        return self.c_proj(h, residual=residual, dropout_p=self.resid_pdrop if self.training else 0.0)
+        return ops.mlp(hidden_states, self.c_fc.weight, self.c_fc.bias, self.c_proj.weight, self.c_proj.bias, act=self.act,
+                       residual=residual, weight_kn=True, dropout_p=self.resid_pdrop if self.training else 0.0)
 
 
 class GPT2Block(nn.Module):

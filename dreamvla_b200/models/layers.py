@@ -78,7 +78,8 @@ class Mlp(nn.Module):
         self.act = act
 
     def forward(self, x, residual=None):
-        return self.fc2(self.fc1(x, act=self.act), residual=residual)
+        _require_bf16(self.fc1.weight, "Mlp")
+        return ops.mlp(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, act=self.act, residual=residual)
 
 
 class Block(nn.Module):

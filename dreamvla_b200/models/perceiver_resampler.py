@@ -67,6 +67,5 @@ class PerceiverResampler(nn.Module):
         latents = self.latents.unsqueeze(0).expand(b * T, -1, -1).contiguous()
         for attn, ff in self.layers:
             latents = attn(x, latents)
-            hmid = ff[1](ff[0](latents), act="gelu_erf")
-            latents = ff[3](hmid, residual=latents)
+            latents = ops.mlp(ff[0](latents), ff[1].weight, None, ff[3].weight, None, act="gelu_erf", residual=latents)
         return self.norm(latents).view(b, T, -1, D)

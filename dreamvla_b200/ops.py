@@ -130,6 +130,57 @@ def linear(x, weight, bias=None, *, act=None, residual=None, weight_kn=False, dr
                          float(dropout_p), float(alpha))
 
 
+class _MLP(torch.autograd.Function):
+    """y = dropout(act(x W1^T + b1) W2^T + b2) + residual with the activation backward fused into the dgrad GEMM of the
+    second layer (epilogue multiplies by act'(pre-activation)): no stand-alone elementwise pass in the backward."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, residual, act, weight_kn, dropout_p):
+        x2 = _as2d(_bf16c(x))
+        need = any(ctx.needs_input_grad)
+        H = w1.shape[1] if weight_kn else w1.shape[0]
+        N = w2.shape[1] if weight_kn else w2.shape[0]
+        aux = torch.empty((x2.shape[0], H), device=x2.device, dtype=torch.bfloat16) if need else None
+        h = L.gemm(x2, w1, b_mn=weight_kn, bias=b1, act=act, aux_out=aux)
+        seed = next_seed() if dropout_p > 0 else 0
+        res2 = _as2d(_bf16c(residual)) if residual is not None else None
+        y = L.gemm(h, w2, b_mn=weight_kn, bias=b2, residual=res2, dropout_p=dropout_p, dropout_seed=seed,
+                   dropout_seed_ptr=seed_counter(x2.device) if dropout_p > 0 else None)
+        if need:
+            ctx.save_for_backward(x2, aux, h)
+        ctx.params = (w1, b1, w2, b2)
+        ctx.meta = (act, weight_kn, dropout_p, seed, x.shape, residual.shape if residual is not None else None)
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, aux, h = ctx.saved_tensors
+        w1, b1, w2, b2 = ctx.params
+        act, weight_kn, dropout_p, seed, xshape, res_shape = ctx.meta
+        dy2 = _as2d(_bf16c(dy))
+        d_res = dy.view(res_shape) if res_shape is not None and ctx.needs_input_grad[5] else None
+        dz2 = L.dropout(dy2, dropout_p, seed, seed_ptr=seed_counter(dy2.device)) if dropout_p > 0 else dy2
+        dh = L.gemm(dz2, w2, b_mn=not weight_kn, aux_in=aux, act=act)          # (dZ2 W2) * act'(pre)
+        dw1 = dw2 = db1 = db2 = dx = None
+        if w2.requires_grad:
+            dw2 = _accum_grad_2d(w2, h, dz2, True, True) if weight_kn else _accum_grad_2d(w2, dz2, h, True, True)
+        if b2 is not None and b2.requires_grad:
+            db2 = _accum_bias_grad(b2, dz2)
+        if ctx.needs_input_grad[0]:
+            dx = L.gemm(dh, w1, b_mn=not weight_kn).view(xshape)
+        if w1.requires_grad:
+            dw1 = _accum_grad_2d(w1, x2, dh, True, True) if weight_kn else _accum_grad_2d(w1, dh, x2, True, True)
+        if b1 is not None and b1.requires_grad:
+            db1 = _accum_bias_grad(b1, dh)
+        return dx, dw1, db1, dw2, db2, d_res, None, None, None
+
+
+def mlp(x, w1, b1, w2, b2, *, act, residual=None, weight_kn=False, dropout_p=0.0):
+    """Two-layer MLP block (timm Mlp / GPT2MLP / Perceiver FeedForward) on two fused-epilogue GEMMs."""
+    return _MLP.apply(x, w1, b1, w2, b2, residual, ACT_IDS[act] if not isinstance(act, int) else act, weight_kn,
+                      float(dropout_p))
+
+
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, eps):

@@ -18,7 +18,7 @@ if what == "gemm":
             L.gemm(A, W, bias=b, act=act, residual=R if act == 0 else None)
     torch.cuda.synchronize()
 else:
-    B, H, Lq = 2, 16, 1290
+    B, H, Lq = (40, 16, 265) if what == "attn_dec" else (2, 16, 1290)
     qkv = torch.randn(B, Lq, 3, H, 64, device=dev, dtype=torch.bfloat16)
     q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
     for _ in range(3):

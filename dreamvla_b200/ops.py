@@ -160,7 +160,10 @@ class _MLP(torch.autograd.Function):
         dy2 = _as2d(_bf16c(dy))
         d_res = dy.view(res_shape) if res_shape is not None and ctx.needs_input_grad[5] else None
         dz2 = L.dropout(dy2, dropout_p, seed, seed_ptr=seed_counter(dy2.device)) if dropout_p > 0 else dy2
-        dh = L.gemm(dz2, w2, b_mn=not weight_kn, aux_in=aux, act=act)          # (dZ2 W2) * act'(pre)
+        # (dZ2 W2) * act'(pre).  The GEMM can apply act' in its epilogue (aux_in), but with 8 epilogue warps per CTA that
+        # made these K=1024 dgrad GEMMs epilogue-bound (+18 % GEMM time, profiles/r1_notes.md); the HBM-bound elementwise
+        # kernel is cheaper until the epilogue is widened.
+        dh = L.act_bwd(L.gemm(dz2, w2, b_mn=not weight_kn), aux, act)
         dw1 = dw2 = db1 = db2 = dx = None
         if w2.requires_grad:
             dw2 = _accum_grad_2d(w2, h, dz2, True, True) if weight_kn else _accum_grad_2d(w2, dz2, h, True, True)

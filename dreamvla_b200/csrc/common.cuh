@@ -327,6 +327,34 @@ __device__ __forceinline__ float act_bwd(float x, int act) {
   }
 }
 
+// v[j] *= act'(x[j]) with the switch hoisted out of the element loop.
+template <int N>
+__device__ __forceinline__ void act_bwd_mul_n(float (&v)[N], const float (&x)[N], int act) {
+  switch (act) {
+    case ACT_GELU_ERF:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] *= act_bwd(x[j], ACT_GELU_ERF);
+      break;
+    case ACT_GELU_TANH:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] *= act_bwd(x[j], ACT_GELU_TANH);
+      break;
+    case ACT_QUICK_GELU:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] *= act_bwd(x[j], ACT_QUICK_GELU);
+      break;
+    case ACT_RELU:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = x[j] > 0.f ? v[j] : 0.f;
+      break;
+    case ACT_SILU:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] *= act_bwd(x[j], ACT_SILU);
+      break;
+    default: break;
+  }
+}
+
 // Counter-based RNG (Philox-4x32-10).  One call yields 4 uniform 32-bit words for (seed, offset).
 __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t offset) {
   uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);

@@ -20,7 +20,8 @@ namespace dvla {
 constexpr int BM = 128;
 constexpr int BK = 64;       // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 16;   // 4 per TMEM lane quadrant: each SM sub-partition interleaves 4 epilogue warps
+constexpr int EPI_STAGE_BYTES = 2048;  // per epilogue warp: 32 rows x 64 B staging panel
 constexpr int GEMM_THREADS = 64 + NUM_EPI_WARPS * 32;
 
 struct GemmParams {
@@ -47,7 +48,7 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int STAGING_BYTES = NUM_EPI_WARPS * 4096;   // per epilogue warp: 32 rows x 128 B
+  static constexpr int STAGING_BYTES = NUM_EPI_WARPS * EPI_STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + BAR_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
 };
@@ -157,32 +158,33 @@ __device__ __forceinline__ void epilogue8(float (&v)[8], int row, int col, const
   }
 }
 
-// ---- staged epilogue: per-warp 32 x 128 B smem panel, 16-byte chunk c of row r stored at chunk c ^ (r & 7) ------------
-// The thread<->row TMEM layout gives each lane 64 contiguous bf16 of ONE row; writing those straight to global costs 32
-// L1 wavefronts per store instruction.  Staging through this swizzled panel turns every global access of the epilogue
-// (output, pre-activation copy, residual) into full 128-byte lines: 4 rows per instruction.
+// ---- staged epilogue: per-warp 32 x 64 B smem panel (32 rows x 32 bf16 columns) ---------------------------------------
+// The thread<->row TMEM layout gives each lane 32 contiguous bf16 of ONE row; writing those straight to global costs 32 L1
+// wavefronts per store instruction.  Staging through this swizzled panel (16-byte chunk c of row r stored at
+// c ^ ((r >> 1) & 3): conflict-free for both the row-wise writes and the 8-rows-per-instruction reads) turns every
+// global access of the epilogue (output, pre-activation copy, residual) into full 64-byte row segments.
 __device__ __forceinline__ uint4* stage_ptr(uint8_t* base, int row, int chunk) {
-  return reinterpret_cast<uint4*>(base + row * 128 + ((chunk ^ (row & 7)) << 4));
+  return reinterpret_cast<uint4*>(base + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
 }
-__device__ __forceinline__ void stage_write_row(uint8_t* base, int lane, const float (&v)[64]) {
+__device__ __forceinline__ void stage_write_row(uint8_t* base, int lane, const float (&v)[32]) {
 #pragma unroll
-  for (int c = 0; c < 8; ++c)
+  for (int c = 0; c < 4; ++c)
     *stage_ptr(base, lane, c) = make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
                                            pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
 }
-// panel (rows row0.., cols col0..col0+63) <-> global [*, ld] bf16; rows >= M and 8-col groups >= N are skipped
+// panel (rows row0.., cols col0..col0+31) <-> global [*, ld] bf16; rows >= M and 8-col groups >= N are skipped
 __device__ __forceinline__ void stage_flush(uint8_t* base, int lane, bf16* g, long long ld, int row0, int col0, int M, int N) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + (lane >> 3), c = lane & 7;
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2), c = lane & 3;
     if (row0 + r < M && col0 + c * 8 < N)
       *reinterpret_cast<uint4*>(g + static_cast<long long>(row0 + r) * ld + col0 + c * 8) = *stage_ptr(base, r, c);
   }
 }
 __device__ __forceinline__ void stage_load(uint8_t* base, int lane, const bf16* g, long long ld, int row0, int col0, int M, int N) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + (lane >> 3), c = lane & 7;
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2), c = lane & 3;
     uint4 val = make_uint4(0, 0, 0, 0);
     if (row0 + r < M && col0 + c * 8 < N)
       val = *reinterpret_cast<const uint4*>(g + static_cast<long long>(row0 + r) * ld + col0 + c * 8);
@@ -190,17 +192,17 @@ __device__ __forceinline__ void stage_load(uint8_t* base, int lane, const bf16* 
   }
 }
 
-// one 64-column panel of one warp: v[64] = this lane's row (row0 + lane), columns col0 .. col0+63
-__device__ __forceinline__ void epilogue_panel_staged(float (&v)[64], uint8_t* stage, int lane, int row0, int col0,
+// one 32-column chunk of one warp: v[32] = this lane's row (row0 + lane), columns col0 .. col0+31
+__device__ __forceinline__ void epilogue_chunk_staged(float (&v)[32], uint8_t* stage, int lane, int row0, int col0,
                                                       const GemmParams& p) {
   const int row = row0 + lane;
   if (p.alpha != 1.0f) {
 #pragma unroll
-    for (int j = 0; j < 64; ++j) v[j] *= p.alpha;
+    for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
   }
   if (p.bias) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < 4; ++c) {
       if (col0 + c * 8 < p.N) {
         const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + c * 8));
         float2 f;
@@ -220,24 +222,26 @@ __device__ __forceinline__ void epilogue_panel_staged(float (&v)[64], uint8_t* s
   if (p.aux_in) {
     stage_load(stage, lane, p.aux_in, p.ld_aux, row0, col0, p.M, p.N);
     __syncwarp();
+    float x[32];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < 4; ++c) {
       const uint4 a = *stage_ptr(stage, lane, c);
       float2 f;
-      f = unpack_bf16x2(a.x); v[8 * c] *= act_bwd(f.x, p.act); v[8 * c + 1] *= act_bwd(f.y, p.act);
-      f = unpack_bf16x2(a.y); v[8 * c + 2] *= act_bwd(f.x, p.act); v[8 * c + 3] *= act_bwd(f.y, p.act);
-      f = unpack_bf16x2(a.z); v[8 * c + 4] *= act_bwd(f.x, p.act); v[8 * c + 5] *= act_bwd(f.y, p.act);
-      f = unpack_bf16x2(a.w); v[8 * c + 6] *= act_bwd(f.x, p.act); v[8 * c + 7] *= act_bwd(f.y, p.act);
+      f = unpack_bf16x2(a.x); x[8 * c] = f.x; x[8 * c + 1] = f.y;
+      f = unpack_bf16x2(a.y); x[8 * c + 2] = f.x; x[8 * c + 3] = f.y;
+      f = unpack_bf16x2(a.z); x[8 * c + 4] = f.x; x[8 * c + 5] = f.y;
+      f = unpack_bf16x2(a.w); x[8 * c + 6] = f.x; x[8 * c + 7] = f.y;
     }
+    act_bwd_mul_n<32>(v, x, p.act);
     __syncwarp();
   } else if (p.act != ACT_NONE) {
-    act_fwd_n<64>(v, p.act);
+    act_fwd_n<32>(v, p.act);
   }
   if (p.drop_scale != 0.f) {
     const uint64_t seed = p.drop_seed + (p.drop_seed_ptr ? __ldg(p.drop_seed_ptr) : 0ull);
     const uint64_t blk0 = static_cast<uint64_t>(row) * static_cast<uint64_t>((p.N + 7) >> 3) + (col0 >> 3);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < 4; ++c) {
       const uint32_t keep = dropout_keep8(seed, blk0 + c, p.drop_thresh);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[8 * c + j] = ((keep >> j) & 1u) ? v[8 * c + j] * p.drop_scale : 0.f;
@@ -247,7 +251,7 @@ __device__ __forceinline__ void epilogue_panel_staged(float (&v)[64], uint8_t* s
     stage_load(stage, lane, reinterpret_cast<const bf16*>(p.residual), p.ldr, row0, col0, p.M, p.N);
     __syncwarp();
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < 4; ++c) {
       const uint4 a = *stage_ptr(stage, lane, c);
       float2 f;
       f = unpack_bf16x2(a.x); v[8 * c] += f.x; v[8 * c + 1] += f.y;
@@ -261,6 +265,51 @@ __device__ __forceinline__ void epilogue_panel_staged(float (&v)[64], uint8_t* s
   __syncwarp();
   stage_flush(stage, lane, reinterpret_cast<bf16*>(p.out), p.ldo, row0, col0, p.M, p.N);
   __syncwarp();
+}
+
+// Epilogue of one output tile for one epilogue warp (shared by the single-CTA and CTA-pair kernels).
+// Warp w (2..17): TMEM lane quadrant w & 3, column quarter (w - 2) >> 2; BN/4 columns in chunks of 32.
+template <int BN, typename ArriveFn>
+__device__ __forceinline__ void epilogue_tile(uint32_t t_acc /* tmem base + acc*BN */, uint8_t* staging, int warp, int lane,
+                                              int m0, int n0, const GemmParams& p, ArriveFn arrive_tmem_free) {
+  const int q = warp & 3;
+  const int quarter = (warp - 2) >> 2;
+  const uint32_t t_lane = t_acc + (static_cast<uint32_t>(q * 32) << 16);
+  uint8_t* stage = staging + (warp - 2) * EPI_STAGE_BYTES;
+  constexpr int CPW = BN / 4 / 32;
+#pragma unroll 1
+  for (int ci = 0; ci < CPW; ++ci) {
+    const int c = quarter * (BN / 4) + ci * 32;
+    uint32_t r[32];
+    tmem_ld_32x32(t_lane + c, r);
+    tmem_ld_wait();
+    if (ci == CPW - 1) {   // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) arrive_tmem_free();
+    }
+    if (n0 + c >= p.N) continue;     // warp-uniform
+    if (p.staged_ok) {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      epilogue_chunk_staged(v, stage, lane, m0 + q * 32, n0 + c, p);
+    } else {
+      const int row = m0 + q * 32 + lane;
+      if (row < p.M) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int col = n0 + c + g * 8;
+          if (col < p.N) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+            epilogue8(v, row, col, p);
+          }
+        }
+      }
+    }
+  }
 }
 
 template <int BN, bool A_MN, bool B_MN>
@@ -367,8 +416,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ------------------------------------------------ epilogue ----------------------------------------------------
-    const int q = warp & 3;              // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;    // which half of the BN columns
     int acc = 0;
     uint32_t acc_ph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -376,59 +423,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int n0 = (tile / p.num_m_tiles) * BN;
       mbar_wait(&tfull_bar[acc], acc_ph);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
-      const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-      constexpr int CHUNKS = BN / 2 / 32;
-      if (p.staged_ok) {
-        uint8_t* stage = staging + (warp - 2) * 4096;
-        constexpr int PANELS = BN / 2 / 64;
-#pragma unroll 1
-        for (int pi = 0; pi < PANELS; ++pi) {
-          const int c = half * (BN / 2) + pi * 64;
-          uint32_t r0[32], r1[32];
-          tmem_ld_32x32(t_lane + c, r0);
-          tmem_ld_32x32(t_lane + c + 32, r1);
-          tmem_ld_wait();
-          if (pi == PANELS - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-          }
-          if (n0 + c < p.N) {      // warp-uniform
-            float v[64];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
-            epilogue_panel_staged(v, stage, lane, m0 + q * 32, n0 + c, p);
-          }
-        }
-        acc ^= 1;
-        if (acc == 0) acc_ph ^= 1;
-        continue;
-      }
-#pragma unroll 1
-      for (int ci = 0; ci < CHUNKS; ++ci) {
-        const int c = half * (BN / 2) + ci * 32;
-        uint32_t r[32];
-        tmem_ld_32x32(t_lane + c, r);
-        tmem_ld_wait();
-        if (ci == CHUNKS - 1) {  // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        }
-        if (row < p.M) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = n0 + c + g * 8;
-            if (col < p.N) {
-              float v[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-              epilogue8(v, row, col, p);
-            }
-          }
-        }
-      }
+      uint64_t* free_bar = &tempty_bar[acc];
+      epilogue_tile<BN>(tmem_base + acc * BN, staging, warp, lane, m0, n0, p, [free_bar] { mbar_arrive(free_bar); });
       acc ^= 1;
       if (acc == 0) acc_ph ^= 1;
     }
@@ -456,7 +452,7 @@ struct Gemm2Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = 6;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int STAGING_BYTES = NUM_EPI_WARPS * 4096;
+  static constexpr int STAGING_BYTES = NUM_EPI_WARPS * EPI_STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + BAR_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
 };
@@ -569,37 +565,15 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
     }
   } else {
-    const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_ph = 0;
-    uint8_t* stage = staging + (warp - 2) * 4096;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       const int m0 = (tile % num_m2) * (2 * BM) + rank * BM;
       const int n0 = (tile / num_m2) * BN;
       mbar_wait(&tfull_bar[acc], acc_ph);
       tc_fence_after();
-      const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-      constexpr int PANELS = BN / 2 / 64;
-#pragma unroll 1
-      for (int pi = 0; pi < PANELS; ++pi) {
-        const int c = half * (BN / 2) + pi * 64;
-        uint32_t r0[32], r1[32];
-        tmem_ld_32x32(t_lane + c, r0);
-        tmem_ld_32x32(t_lane + c + 32, r1);
-        tmem_ld_wait();
-        if (pi == PANELS - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
-        }
-        if (n0 + c < p.N) {
-          float v[64];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
-          epilogue_panel_staged(v, stage, lane, m0 + q * 32, n0 + c, p);
-        }
-      }
+      uint64_t* free_bar = &tempty_bar[acc];
+      epilogue_tile<BN>(tmem_base + acc * BN, staging, warp, lane, m0, n0, p, [free_bar] { mbar_arrive_leader(free_bar); });
       acc ^= 1;
       if (acc == 0) acc_ph ^= 1;
     }

@@ -69,13 +69,36 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
   for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
 }
 
+// 32-column half-row helpers for the 256-thread kernels (threads t and t+128 share row t, columns [32*half, 32*half+32))
+__device__ __forceinline__ void write_row32(uint8_t* tile, int r, int half, const float (&v)[32]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<uint4*>(tile + r * 128 + (((half * 4 + c) ^ (r & 7)) << 4)) =
+        make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
+                   pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
+}
+__device__ __forceinline__ void store_row32(bf16* dst, const float (&v)[32], float scale) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<uint4*>(dst + c * 8) =
+        make_uint4(pack_bf16x2(v[8 * c] * scale, v[8 * c + 1] * scale), pack_bf16x2(v[8 * c + 2] * scale, v[8 * c + 3] * scale),
+                   pack_bf16x2(v[8 * c + 4] * scale, v[8 * c + 5] * scale), pack_bf16x2(v[8 * c + 6] * scale, v[8 * c + 7] * scale));
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  tmem_ld_32x32(taddr, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+
 // ============================================================ dK / dV ==============================================================
 constexpr int KV_SM_K = 0, KV_SM_V = 16384, KV_SM_Q = 32768, KV_SM_DO = KV_SM_Q + 2 * 8192, KV_SM_P = KV_SM_DO + 2 * 8192,
               KV_SM_DS = KV_SM_P + 16384, KV_SM_LSE = KV_SM_DS + 16384, KV_SM_FLAGS = KV_SM_LSE + 2 * 2 * 64 * 4,
               KV_SM_BAR = KV_SM_FLAGS + 512;
 constexpr int ATTN_DKV_SMEM = KV_SM_BAR + 128 + 1024;
 
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(256, 2)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                        const AttnBwdTcParams p) {
@@ -90,9 +113,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 5);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rowi = tid & 127;          // key row of the tile owned by this thread (shared with thread tid ^ 128)
+  const int half = tid >> 7;           // which 32 of the 64 query columns / output columns
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int k0 = kt * 128;
-  const int key = k0 + tid;
+  const int key = k0 + rowi;
   const int nqt = (p.Lq + 63) / 64;
   const long long bh = static_cast<long long>(b) * p.H + h;
 
@@ -106,12 +131,12 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t lane_off = (static_cast<uint32_t>((warp & 3) * 32) << 16) + half * 32;   // TMEM lane quadrant + column half
   const uint32_t tS = tmem_base, tDP = tmem_base + 64, tDV = tmem_base + 128, tDK = tmem_base + 192;
 
   // per-(64-query tile) flag of this 128-key tile, computed once into smem: 0 skip, 1 partial, 2 full
   uint8_t* s_flags = smem + KV_SM_FLAGS;
-  for (int qi = tid; qi < nqt && qi < 512; qi += 128) {
+  for (int qi = tid; qi < nqt && qi < 512; qi += 256) {
     int f = 2;
     if (p.tile_flags) {
       int any = 0, all = 1;
@@ -158,20 +183,19 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   // software prefetch of the per-tile scalars (lse, delta for tid < 64; transposed mask words for every key row): the
   // global loads of tile j+1 are issued at the top of iteration j and consumed at the top of iteration j+1
   float pf_lse = INFINITY, pf_delta = 0.f;
-  uint32_t pf_w0 = 0xffffffffu, pf_w1 = 0xffffffffu;
+  uint32_t pf_w = 0xffffffffu;         // transposed mask word covering this thread's 32 queries of the next tile
   auto prefetch = [&](int qtile) {
     if (tid < 64) {
       const int qi = qtile * 64 + tid;
       pf_lse = (qi < p.Lq) ? p.lse[bh * p.Lq + qi] * B_LOG2E : INFINITY;
       pf_delta = (qi < p.Lq) ? p.delta[bh * p.Lq + qi] : 0.f;
     }
-    pf_w0 = pf_w1 = 0xffffffffu;
+    pf_w = 0xffffffffu;
     if (s_flags[qtile] == 1) {
-      const int wi = qtile * 2;
-      pf_w0 = (key < p.Lk && wi < p.mask_t_words) ? p.mask_t[static_cast<long long>(key) * p.mask_t_words + wi] : 0u;
-      pf_w1 = (key < p.Lk && wi + 1 < p.mask_t_words) ? p.mask_t[static_cast<long long>(key) * p.mask_t_words + wi + 1] : 0u;
+      const int wi = qtile * 2 + half;
+      pf_w = (key < p.Lk && wi < p.mask_t_words) ? p.mask_t[static_cast<long long>(key) * p.mask_t_words + wi] : 0u;
     }
-    if (key >= p.Lk) { pf_w0 = 0u; pf_w1 = 0u; }
+    if (key >= p.Lk) pf_w = 0u;
   };
   if (qt < nqt) prefetch(qt);
   while (qt < nqt) {
@@ -181,7 +205,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       s_lse[st * 64 + tid] = pf_lse;
       s_delta[st * 64 + tid] = pf_delta;
     }
-    const uint32_t w0 = pf_w0, w1 = pf_w1;
+    const uint32_t wv = pf_w;
     if (qt_next < nqt) prefetch(qt_next);
     if (tid == 0) {
       if (qt_next < nqt) load_q(qt_next, st ^ 1);
@@ -205,24 +229,24 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     ph_s ^= 1;
     tc_fence_after();
 
-    // visibility of (query c, this key) for the 64 queries of the tile: w0 / w1 = two words of the transposed bit matrix
-    float sv[64], dpv[64];
-    tmem_ld64(tS + lane_off, sv);
-    tmem_ld64(tDP + lane_off, dpv);
-    const float* lse_t = s_lse + st * 64;
-    const float* dl_t = s_delta + st * 64;
-    uint32_t keepm[8];                               // dropout: lane (key%8 == r) owns queries c == r (mod 8)
+    // visibility of (query c, this key) for this thread's 32 queries: bits of wv (transposed bit matrix)
+    float sv[32], dpv[32];
+    tmem_ld32(tS + lane_off, sv);
+    tmem_ld32(tDP + lane_off, dpv);
+    const float* lse_t = s_lse + st * 64 + half * 32;
+    const float* dl_t = s_delta + st * 64 + half * 32;
+    uint32_t keepm[4];                               // dropout: lane (key%8 == r) owns queries c == r (mod 8)
     if (p.drop_scale != 0.f) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const long long qc = q0 + (lane & 7) + i * 8;
+      for (int i = 0; i < 4; ++i) {
+        const long long qc = q0 + half * 32 + (lane & 7) + i * 8;
         keepm[i] = dropout_keep8(seed, (bh * p.Lq + qc) * nblk + (key >> 3), p.drop_thresh);
       }
     }
 #pragma unroll
-    for (int c = 0; c < 64; ++c) {
-      const bool vis = ((c < 32 ? w0 : w1) >> (c & 31)) & 1u;
-      float pv = vis ? ex2_approx(fmaf(sv[c], sc, -lse_t[c])) : 0.f;       // lse = +inf for padded queries -> 0
+    for (int c = 0; c < 32; ++c) {
+      const bool vis = (wv >> c) & 1u;
+      const float pv = vis ? ex2_approx(fmaf(sv[c], sc, -lse_t[c])) : 0.f;       // lse = +inf for padded queries -> 0
       float dp = dpv[c];
       if (p.drop_scale != 0.f) {
         const uint32_t m = __shfl_sync(0xffffffffu, keepm[c >> 3], (lane & ~7) | (c & 7));
@@ -235,8 +259,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         sv[c] = pv;
       }
     }
-    write_row64(smem + KV_SM_P, tid, sv);            // P^T  (dropped) -> A operand for dV
-    write_row64(smem + KV_SM_DS, tid, dpv);          // dS^T           -> A operand for dK
+    write_row32(smem + KV_SM_P, rowi, half, sv);     // P^T  (dropped) -> A operand for dV
+    write_row32(smem + KV_SM_DS, rowi, half, dpv);   // dS^T           -> A operand for dK
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -262,14 +286,14 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     st ^= 1;
   }
 
-  {   // TMEM loads are warp-collective: every lane executes them, only in-range key rows store
-    float v[64];
+  {   // TMEM loads are warp-collective: every lane executes them, only in-range key rows store (32 of 64 columns each)
+    float v[32];
 #pragma unroll
-    for (int j = 0; j < 64; ++j) v[j] = 0.f;
-    if (any_iter) tmem_ld64(tDV + lane_off, v);
-    if (key < p.Lk) store_row64(p.dv + b * p.dv_sb + static_cast<long long>(key) * p.dv_ss + h * p.dv_sh, v, 1.0f);
-    if (any_iter) tmem_ld64(tDK + lane_off, v);
-    if (key < p.Lk) store_row64(p.dk + b * p.dk_sb + static_cast<long long>(key) * p.dk_ss + h * p.dk_sh, v, p.scale);
+    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    if (any_iter) tmem_ld32(tDV + lane_off, v);
+    if (key < p.Lk) store_row32(p.dv + b * p.dv_sb + static_cast<long long>(key) * p.dv_ss + h * p.dv_sh + half * 32, v, 1.0f);
+    if (any_iter) tmem_ld32(tDK + lane_off, v);
+    if (key < p.Lk) store_row32(p.dk + b * p.dk_sb + static_cast<long long>(key) * p.dk_ss + h * p.dk_sh + half * 32, v, p.scale);
   }
   tc_fence_before();
   __syncthreads();
@@ -282,7 +306,7 @@ constexpr int DQ_SM_Q = 0, DQ_SM_DO = 16384, DQ_SM_K = 32768, DQ_SM_V = DQ_SM_K 
               DQ_SM_FLAGS = DQ_SM_DS + 16384, DQ_SM_BAR = DQ_SM_FLAGS + 512;
 constexpr int ATTN_DQ_SMEM = DQ_SM_BAR + 128 + 1024;
 
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(256, 2)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                       const AttnBwdTcParams p) {
@@ -295,9 +319,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 5);
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int rowi = tid & 127, half = tid >> 7;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q0 = qt * 128;
-  const int row = q0 + tid;
+  const int row = q0 + rowi;
   const int nkt = (p.Lk + 63) / 64;
   const long long bh = static_cast<long long>(b) * p.H + h;
 
@@ -311,11 +336,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t lane_off = (static_cast<uint32_t>((warp & 3) * 32) << 16) + half * 32;
   const uint32_t tS = tmem_base, tDP = tmem_base + 64, tDQ = tmem_base + 128;
 
   uint8_t* s_flags = smem + DQ_SM_FLAGS;       // per-(64-key tile) flag of this 128-query tile
-  for (int ki = tid; ki < nkt && ki < 512; ki += 128) {
+  for (int ki = tid; ki < nkt && ki < 512; ki += 256) {
     int f = 2;
     if (p.tile_flags) {
       int any = 0, all = 1;
@@ -360,20 +385,19 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   int st = 0;
   uint32_t ph_kv0 = 0, ph_kv1 = 0, ph_s = 0, ph_o = 0;
   bool first = true, any_iter = false;
-  uint32_t pf_w0 = 0xffffffffu, pf_w1 = 0xffffffffu;     // mask words of the NEXT tile (software prefetch)
+  uint32_t pf_w = 0xffffffffu;     // mask word of this thread's 32 keys of the NEXT tile (software prefetch)
   auto prefetch = [&](int ktile) {
-    pf_w0 = pf_w1 = 0xffffffffu;
+    pf_w = 0xffffffffu;
     if (s_flags[ktile] == 1) {
-      const int wi = ktile * 2;
-      pf_w0 = (row < p.Lq && wi < p.mask_words) ? p.mask[static_cast<long long>(row) * p.mask_words + wi] : 0u;
-      pf_w1 = (row < p.Lq && wi + 1 < p.mask_words) ? p.mask[static_cast<long long>(row) * p.mask_words + wi + 1] : 0u;
+      const int wi = ktile * 2 + half;
+      pf_w = (row < p.Lq && wi < p.mask_words) ? p.mask[static_cast<long long>(row) * p.mask_words + wi] : 0u;
     }
   };
   if (kt < nkt) prefetch(kt);
   while (kt < nkt) {
     const int kt_next = next_tile(kt + 1);
     const int k0 = kt * 64;
-    uint32_t w0 = pf_w0, w1 = pf_w1;
+    uint32_t wv = pf_w;
     if (kt_next < nkt) prefetch(kt_next);
     if (tid == 0) {
       if (kt_next < nkt) load_kv(kt_next, st ^ 1);
@@ -396,29 +420,28 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     ph_s ^= 1;
     tc_fence_after();
 
-    if (k0 + 64 > p.Lk) {
-      const int n0 = p.Lk - k0;                      // valid keys in this tile (1..63)
-      w0 &= (n0 >= 32) ? 0xffffffffu : ((1u << n0) - 1u);
-      w1 &= (n0 <= 32) ? 0u : ((1u << (n0 - 32)) - 1u);
+    {
+      const int nv = p.Lk - (k0 + half * 32);          // valid keys among this thread's 32
+      if (nv < 32) wv &= (nv <= 0) ? 0u : ((1u << nv) - 1u);
     }
-    float sv[64], dpv[64];
-    tmem_ld64(tS + lane_off, sv);
-    tmem_ld64(tDP + lane_off, dpv);
+    float sv[32], dpv[32];
+    tmem_ld32(tS + lane_off, sv);
+    tmem_ld32(tDP + lane_off, dpv);
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
+    for (int g = 0; g < 4; ++g) {
       uint32_t keep = 0xffu;
-      if (p.drop_scale != 0.f) keep = dropout_keep8(seed, (bh * p.Lq + row) * nblk + (k0 >> 3) + g, p.drop_thresh);
+      if (p.drop_scale != 0.f) keep = dropout_keep8(seed, (bh * p.Lq + row) * nblk + ((k0 + half * 32) >> 3) + g, p.drop_thresh);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int c = g * 8 + j;
-        const bool vis = ((c < 32 ? w0 : w1) >> (c & 31)) & 1u;
+        const bool vis = (wv >> c) & 1u;
         const float pv = vis ? ex2_approx(fmaf(sv[c], sc, -lse2)) : 0.f;
         float dp = dpv[c];
         if (p.drop_scale != 0.f) dp = ((keep >> j) & 1u) ? dp * p.drop_scale : 0.f;
         sv[c] = pv * (dp - dlt);
       }
     }
-    write_row64(smem + DQ_SM_DS, tid, sv);
+    write_row32(smem + DQ_SM_DS, rowi, half, sv);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -439,13 +462,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     st ^= 1;
   }
   {
-    float v[64];
-    if (any_iter) tmem_ld64(tDQ + lane_off, v);
-    else {
+    float v[32];
 #pragma unroll
-      for (int j = 0; j < 64; ++j) v[j] = 0.f;
-    }
-    if (row < p.Lq) store_row64(p.dq + b * p.dq_sb + static_cast<long long>(row) * p.dq_ss + h * p.dq_sh, v, p.scale);
+    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    if (any_iter) tmem_ld32(tDQ + lane_off, v);
+    if (row < p.Lq) store_row32(p.dq + b * p.dq_sb + static_cast<long long>(row) * p.dq_ss + h * p.dq_sh + half * 32, v, p.scale);
   }
   tc_fence_before();
   __syncthreads();
@@ -513,12 +534,12 @@ int attn_bwd_tc_dispatch(const dvla_attn_bwd_args* a, const uint32_t* mask_t, in
   if (!make_tmap_rows_b(&k64, a->k, a->Lk, a->H, a->B, a->k_ss, a->k_sh, a->k_sb, 64, &hi)) return DVLA_ERR_CUDA;
   if (!make_tmap_rows_b(&v64, a->v, a->Lk, a->H, a->B, a->v_ss, a->v_sh, a->v_sb, 64, &hi)) return DVLA_ERR_CUDA;
   dim3 gkv((unsigned)((a->Lk + 127) / 128), (unsigned)a->H, (unsigned)a->B);
-  attn_bwd_dkv_tc_kernel<<<gkv, 128, ATTN_DKV_SMEM, s>>>(q64, k128, v128, do64, p);
+  attn_bwd_dkv_tc_kernel<<<gkv, 256, ATTN_DKV_SMEM, s>>>(q64, k128, v128, do64, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("attn_bwd_dkv_tc launch: %s", cudaGetErrorString(e)); return DVLA_ERR_CUDA; }
   count_launch();
   dim3 gq((unsigned)((a->Lq + 127) / 128), (unsigned)a->H, (unsigned)a->B);
-  attn_bwd_dq_tc_kernel<<<gq, 128, ATTN_DQ_SMEM, s>>>(q128, k64, v64, do128, p);
+  attn_bwd_dq_tc_kernel<<<gq, 256, ATTN_DQ_SMEM, s>>>(q128, k64, v64, do128, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("attn_bwd_dq_tc launch: %s", cudaGetErrorString(e)); return DVLA_ERR_CUDA; }
   count_launch();

@@ -256,6 +256,10 @@ def run_ours(args):
             tm += cnt * per
             fl += cnt * 2.0 * M * N * K
             n_tc += cnt
+            if os.environ.get("DVLA_BENCH_DUMP"):
+                print(f"[gemm] M={M:6d} N={N:5d} K={K:5d} a_mn={int(a_mn)} b_mn={int(b_mn)} bias={int(hb)} act={act} res={int(hr)} "
+                      f"aux={int(ha)} drop={int(hd)} n={cnt:4d} {per*1e3:8.1f} us {2.0*M*N*K/per/1e9:7.0f} TF/s total {cnt*per:7.3f} ms",
+                      file=sys.stderr, flush=True)
         peak, how = measured_peaks()
         ach = fl / (tm * 1e-3) / 1e12 if tm > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (every tcgen05 GEMM launch of one fwd+bwd)",

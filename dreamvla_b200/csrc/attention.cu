@@ -629,13 +629,14 @@ int attn_fwd_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s) {
 }
 
 int attn_bwd_tc_dispatch(const dvla_attn_bwd_args* a, const uint32_t* mask_t, int mask_t_words, cudaStream_t s);  // attention_bwd_tc.cu
+int attn_bwd_pipe_dispatch(const dvla_attn_bwd_args* a, const uint32_t* mask_t, int mask_t_words, cudaStream_t s);  // attention_bwd_pipe.cu
 
 // 0 = auto (tcgen05 kernels when both sequences are >= 96 long), 1 = force mma.sync, 2 = force tcgen05
 static int attn_bwd_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("DVLA_ATTN_BWD");
-    mode = (e && !strcmp(e, "legacy")) ? 1 : (e && !strcmp(e, "tc")) ? 2 : 0;
+    mode = (e && !strcmp(e, "legacy")) ? 1 : (e && !strcmp(e, "tc")) ? 2 : (e && !strcmp(e, "pipe")) ? 3 : 0;
   }
   return mode;
 }
@@ -676,6 +677,10 @@ int attn_bwd_dispatch(const dvla_attn_bwd_args* a, cudaStream_t s) {
   attn_delta_kernel<<<(unsigned)((rows * 8 + 255) / 256), 256, 0, s>>>(p);
   DVLA_CHECK_LAUNCH("attn_delta");
   const int bmode = attn_bwd_mode();
+  if (bmode == 3) {      // warp-specialised pipelined tcgen05 kernels
+    const int rc = attn_bwd_pipe_dispatch(a, a->mask_t, a->mask_t_words, s);
+    if (rc != DVLA_ERR_UNSUPPORTED) return rc;
+  }
   if (bmode == 2 || (bmode == 0 && a->Lq >= 96 && a->Lk >= 96)) {
     const int rc = attn_bwd_tc_dispatch(a, a->mask_t, a->mask_t_words, s);
     if (rc != DVLA_ERR_UNSUPPORTED) return rc;

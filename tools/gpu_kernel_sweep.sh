@@ -11,7 +11,7 @@ for g in ${CHECK_GROUPS:-gemm_basic gemm_epilogue gemm_big norm attn loss}; do
   grep -E "TFLOP|us" gpurun_out/check_$g.log | grep PASS | head -20
 done
 if [[ " ${CHECK_GROUPS:-attn} " == *" attn "* ]]; then
-  for cfg in "DVLA_ATTN_FWD=legacy DVLA_ATTN_BWD=legacy" "DVLA_ATTN_FWD=tc DVLA_ATTN_BWD=tc"; do
+  for cfg in "DVLA_ATTN_FWD=legacy DVLA_ATTN_BWD=legacy" "DVLA_ATTN_FWD=tc DVLA_ATTN_BWD=tc" "DVLA_ATTN_FWD=legacy DVLA_ATTN_BWD=pipe"; do
     echo "=== attn ($cfg)"
     env $cfg timeout ${GROUP_TIMEOUT:-240} python tools/gpu_kernel_check.py attn > "gpurun_out/check_attn_${cfg// /_}.log" 2>&1
     grep -E "FAIL|GROUP|Error|watchdog" "gpurun_out/check_attn_${cfg// /_}.log" | head -20

@@ -580,14 +580,15 @@ static bool strides_ok(const void* ptr, long long sb, long long ss, long long sh
   return ptr && (reinterpret_cast<uintptr_t>(ptr) % 16 == 0) && sb % 8 == 0 && ss % 8 == 0 && sh % 8 == 0;
 }
 
-int attn_fwd_tc_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s);   // attention_tc.cu (tcgen05 / TMEM)
+int attn_fwd_tc_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s);   // attention_tc.cu (tcgen05 / TMEM, single-role CTA)
+int attn_fwd_ws_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s);   // attention_fwd_ws.cu (tcgen05, warp-specialised)
 
 // 0 = auto (tcgen05 kernel for Lq >= 96, mma.sync kernel for short query blocks), 1 = force mma.sync, 2 = force tcgen05
 static int attn_fwd_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("DVLA_ATTN_FWD");
-    mode = (e && !strcmp(e, "legacy")) ? 1 : (e && !strcmp(e, "tc")) ? 2 : 0;
+    mode = (e && !strcmp(e, "legacy")) ? 1 : (e && !strcmp(e, "tc")) ? 2 : (e && !strcmp(e, "ws")) ? 3 : 0;
   }
   return mode;
 }
@@ -604,9 +605,13 @@ int attn_fwd_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s) {
   if (a->mask && a->mask_words * 32 < a->Lk) { set_error("attn_fwd: mask_words too small"); return DVLA_ERR_INVALID; }
   if (a->mask && !a->tile_flags) { set_error("attn_fwd: mask given without tile_flags"); return DVLA_ERR_INVALID; }
   const int mode = attn_fwd_mode();
-  if (mode == 2) {   // the tcgen05 forward is parity-green but not yet faster than the mma.sync kernel: opt-in
+  if (mode == 2) {   // the single-role tcgen05 forward is parity-green but slower than the mma.sync kernel: opt-in
     const int rc = attn_fwd_tc_dispatch(a, s);
     if (rc != DVLA_ERR_UNSUPPORTED) return rc;      // strides a tensor map cannot express -> mma.sync kernel below
+  }
+  if (mode == 3) {
+    const int rc = attn_fwd_ws_dispatch(a, s);
+    if (rc != DVLA_ERR_UNSUPPORTED) return rc;
   }
   AttnParams p;
   memset(&p, 0, sizeof(p));
@@ -630,13 +635,14 @@ int attn_fwd_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s) {
 
 int attn_bwd_tc_dispatch(const dvla_attn_bwd_args* a, const uint32_t* mask_t, int mask_t_words, cudaStream_t s);  // attention_bwd_tc.cu
 int attn_bwd_pipe_dispatch(const dvla_attn_bwd_args* a, const uint32_t* mask_t, int mask_t_words, cudaStream_t s);  // attention_bwd_pipe.cu
+int attn_bwd_ws_dispatch(const dvla_attn_bwd_args* a, const uint32_t* mask_t, int mask_t_words, cudaStream_t s);    // attention_bwd_ws.cu
 
 // 0 = auto (tcgen05 kernels when both sequences are >= 96 long), 1 = force mma.sync, 2 = force tcgen05
 static int attn_bwd_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("DVLA_ATTN_BWD");
-    mode = (e && !strcmp(e, "legacy")) ? 1 : (e && !strcmp(e, "tc")) ? 2 : (e && !strcmp(e, "pipe")) ? 3 : 0;
+    mode = (e && !strcmp(e, "legacy")) ? 1 : (e && !strcmp(e, "tc")) ? 2 : (e && !strcmp(e, "pipe")) ? 3 : (e && !strcmp(e, "ws")) ? 4 : 0;
   }
   return mode;
 }
@@ -679,6 +685,10 @@ int attn_bwd_dispatch(const dvla_attn_bwd_args* a, cudaStream_t s) {
   const int bmode = attn_bwd_mode();
   if (bmode == 3) {      // warp-specialised pipelined tcgen05 kernels
     const int rc = attn_bwd_pipe_dispatch(a, a->mask_t, a->mask_t_words, s);
+    if (rc != DVLA_ERR_UNSUPPORTED) return rc;
+  }
+  if (bmode == 4) {      // warp-specialised tcgen05 kernels, 2 CTAs / SM (attention_bwd_ws.cu)
+    const int rc = attn_bwd_ws_dispatch(a, a->mask_t, a->mask_t_words, s);
     if (rc != DVLA_ERR_UNSUPPORTED) return rc;
   }
   if (bmode == 2 || (bmode == 0 && a->Lq >= 96 && a->Lk >= 96)) {

@@ -34,6 +34,8 @@ struct GemmParams {
   long long ldo, ldr, ld_aux;
   int num_m_tiles, num_n_tiles, num_k_blocks;
   int act, out_fp32, vec_ok, staged_ok;
+  int k_splits, kb_per_split;   // split-K: work unit = (tile, split), each covering kb_per_split k-blocks
+  int atomic_out;               // epilogue = out += v with red.global.add.bf16x2 (split-K accumulate into a gradient)
   float alpha;
   float drop_scale;        // 1/(1-p_eff), 0 => dropout disabled
   uint32_t drop_thresh;    // round(p*65536)
@@ -181,6 +183,19 @@ __device__ __forceinline__ void stage_flush(uint8_t* base, int lane, bf16* g, lo
       *reinterpret_cast<uint4*>(g + static_cast<long long>(row0 + r) * ld + col0 + c * 8) = *stage_ptr(base, r, c);
   }
 }
+// out += panel with one 16-byte vector reduction per 8 columns (REDG.E.ADD.BF16x8)
+__device__ __forceinline__ void stage_flush_atomic(uint8_t* base, int lane, bf16* g, long long ld, int row0, int col0, int M, int N) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2), c = lane & 3;
+    if (row0 + r < M && col0 + c * 8 < N) {
+      const uint4 v = *stage_ptr(base, r, c);
+      asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};"
+                   :: "l"(g + static_cast<long long>(row0 + r) * ld + col0 + c * 8), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                   : "memory");
+    }
+  }
+}
 __device__ __forceinline__ void stage_load(uint8_t* base, int lane, const bf16* g, long long ld, int row0, int col0, int M, int N) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -263,7 +278,8 @@ __device__ __forceinline__ void epilogue_chunk_staged(float (&v)[32], uint8_t* s
   }
   stage_write_row(stage, lane, v);
   __syncwarp();
-  stage_flush(stage, lane, reinterpret_cast<bf16*>(p.out), p.ldo, row0, col0, p.M, p.N);
+  if (p.atomic_out) stage_flush_atomic(stage, lane, reinterpret_cast<bf16*>(p.out), p.ldo, row0, col0, p.M, p.N);
+  else              stage_flush(stage, lane, reinterpret_cast<bf16*>(p.out), p.ldo, row0, col0, p.M, p.N);
   __syncwarp();
 }
 
@@ -351,16 +367,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int total_units = total_tiles * p.k_splits;
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer ------------------------------------------------
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        const int tile = unit % total_tiles;
         const int m0 = (tile % p.num_m_tiles) * BM;
         const int n0 = (tile / p.num_m_tiles) * BN;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        const int kb0 = (unit / total_tiles) * p.kb_per_split;
+        const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
           uint8_t* a_dst = sA + s * Cfg::A_BYTES;
@@ -389,11 +409,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t ph = 0;
       int acc = 0;
       uint32_t acc_ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        const int kb0 = (unit / total_tiles) * p.kb_per_split;
+        const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t a_base = smem_u32(sA + s * Cfg::A_BYTES);
@@ -404,7 +426,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                          : make_smem_desc_sw128(a_base + k * (UMMA_K * 2), 16, 1024);
             const uint64_t b_desc = B_MN ? make_smem_desc_sw128(b_base + k * (UMMA_K * 128), BK * 128, 1024)
                                          : make_smem_desc_sw128(b_base + k * (UMMA_K * 2), 16, 1024);
-            umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
@@ -418,7 +440,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ------------------------------------------------ epilogue ----------------------------------------------------
     int acc = 0;
     uint32_t acc_ph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      const int tile = unit % total_tiles;
       const int m0 = (tile % p.num_m_tiles) * BM;
       const int n0 = (tile / p.num_m_tiles) * BN;
       mbar_wait(&tfull_bar[acc], acc_ph);
@@ -500,6 +523,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   const int num_m2 = (p.M + 2 * BM - 1) / (2 * BM);
   const int total_tiles = num_m2 * p.num_n_tiles;
+  const int total_units = total_tiles * p.k_splits;
   const int num_clusters = gridDim.x >> 1;
   const int cluster_id = blockIdx.x >> 1;
 
@@ -507,10 +531,13 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      for (int unit = cluster_id; unit < total_units; unit += num_clusters) {
+        const int tile = unit % total_tiles;
         const int m0 = (tile % num_m2) * (2 * BM) + rank * BM;
         const int n0 = (tile / num_m2) * BN + rank * 128;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        const int kb0 = (unit / total_tiles) * p.kb_per_split;
+        const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           if (leader) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
           else        mbar_arrive_leader(&full_bar[s]);
@@ -539,11 +566,13 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       uint32_t ph = 0;
       int acc = 0;
       uint32_t acc_ph = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      for (int unit = cluster_id; unit < total_units; unit += num_clusters) {
         mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        const int kb0 = (unit / total_tiles) * p.kb_per_split;
+        const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t a_base = smem_u32(sA + s * Cfg::A_BYTES);
@@ -554,7 +583,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                                          : make_smem_desc_sw128(a_base + k * (UMMA_K * 2), 16, 1024);
             const uint64_t b_desc = B_MN ? make_smem_desc_sw128(b_base + k * (UMMA_K * 128), BK * 128, 1024)
                                          : make_smem_desc_sw128(b_base + k * (UMMA_K * 2), 16, 1024);
-            umma_bf16_ss_2cta(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_ss_2cta(d_tmem, a_desc, b_desc, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
           umma_commit_2cta(&empty_bar[s]);
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
@@ -567,7 +596,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   } else {
     int acc = 0;
     uint32_t acc_ph = 0;
-    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+    for (int unit = cluster_id; unit < total_units; unit += num_clusters) {
+      const int tile = unit % total_tiles;
       const int m0 = (tile % num_m2) * (2 * BM) + rank * BM;
       const int n0 = (tile / num_m2) * BN;
       mbar_wait(&tfull_bar[acc], acc_ph);
@@ -703,7 +733,7 @@ static int launch_tc(const dvla_gemm_args* a, const GemmParams& p, cudaStream_t 
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return DVLA_ERR_CUDA; }
     attr_set = true;
   }
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
   cudaError_t e = cudaGetLastError();
@@ -727,7 +757,7 @@ static int launch_tc2(const dvla_gemm_args* a, const GemmParams& p, cudaStream_t
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(2cta smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return DVLA_ERR_CUDA; }
     attr_set = true;
   }
-  const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * p.num_n_tiles;
+  const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * p.num_n_tiles * p.k_splits;
   const int max_clusters = num_sms() / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   kern<<<2 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
@@ -745,6 +775,13 @@ static int gemm_mode() {
     mode = (e && !strcmp(e, "1cta")) ? 1 : (e && !strcmp(e, "2cta")) ? 2 : 0;
   }
   return mode;
+}
+
+// DVLA_GEMM_SPLITK=0 disables the atomic split-K path (bit-reproducible gradient accumulation order)
+static bool splitk_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("DVLA_GEMM_SPLITK"); on = (e && !strcmp(e, "0")) ? 0 : 1; }
+  return on == 1;
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -796,6 +833,61 @@ int gemm_dispatch(const dvla_gemm_args* a, cudaStream_t stream) {
     return DVLA_OK;
   }
   const int sms = num_sms();
+  p.k_splits = 1;
+  p.kb_per_split = p.num_k_blocks;
+  // Split-K for pure accumulations (out += A.B: the weight-gradient GEMMs, few output tiles and a very long contraction):
+  // work unit = (tile, k-range), partial sums added with red.global.add.bf16x2.  Pick the (kernel, split) pair with the
+  // lowest modelled time = waves x (k-blocks per unit + fixed per-unit cost) x per-k-block tile cost.
+  const bool accum_only = p.staged_ok && a->residual == a->out && a->ldr == a->ldo && !a->bias && !a->aux_in &&
+                          !a->aux_out && a->act == DVLA_ACT_NONE && a->dropout_p == 0.f;
+  if (accum_only && splitk_enabled() && gemm_mode() == 0 && p.num_k_blocks >= 32) {
+    const int smax = p.num_k_blocks / 16 < 16 ? p.num_k_blocks / 16 : 16;
+    const long long tl[3] = {(long long)((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + 255) / 256),
+                             (long long)p.num_m_tiles * ((p.N + 255) / 256), (long long)p.num_m_tiles * ((p.N + 127) / 128)};
+    const int slots[3] = {sms / 2, sms, sms};
+    const float w[3] = {1.7f, 1.8f, 1.0f};
+    const float c0 = 8.f;
+    float best = 1e30f; int best_cfg = -1, best_s = 1;
+    for (int cfg = 0; cfg < 3; ++cfg) {
+      if (cfg < 2 && p.N <= 128) continue;
+      for (int sp = 1; sp <= smax; ++sp) {
+        const int kbps = (p.num_k_blocks + sp - 1) / sp;
+        const int se = (p.num_k_blocks + kbps - 1) / kbps;
+        if (se != sp) continue;
+        const long long waves = (tl[cfg] * sp + slots[cfg] - 1) / slots[cfg];
+        const float t = (float)waves * ((float)kbps + c0) * w[cfg];
+        if (t < best * 0.97f || best_cfg < 0) { best = t; best_cfg = cfg; best_s = sp; }
+      }
+    }
+    if (best_s > 1) {
+      p.k_splits = best_s;
+      p.kb_per_split = (p.num_k_blocks + best_s - 1) / best_s;
+      p.atomic_out = 1;
+      p.residual = nullptr;
+      const int key2 = (a->a_mn_major ? 2 : 0) | (a->b_mn_major ? 1 : 0);
+      if (best_cfg == 0) {
+        p.num_n_tiles = (p.N + 255) / 256;
+        switch (key2) {
+          case 0: return launch_tc2<false, false>(a, p, stream);
+          case 1: return launch_tc2<false, true>(a, p, stream);
+          case 2: return launch_tc2<true, false>(a, p, stream);
+          default: return launch_tc2<true, true>(a, p, stream);
+        }
+      }
+      const int bn = best_cfg == 1 ? 256 : 128;
+      p.num_n_tiles = (p.N + bn - 1) / bn;
+      switch ((best_cfg == 1 ? 4 : 0) | key2) {
+        case 0: return launch_tc<128, false, false>(a, p, stream);
+        case 1: return launch_tc<128, false, true>(a, p, stream);
+        case 2: return launch_tc<128, true, false>(a, p, stream);
+        case 3: return launch_tc<128, true, true>(a, p, stream);
+        case 4: return launch_tc<256, false, false>(a, p, stream);
+        case 5: return launch_tc<256, false, true>(a, p, stream);
+        case 6: return launch_tc<256, true, false>(a, p, stream);
+        default: return launch_tc<256, true, true>(a, p, stream);
+      }
+    }
+  }
   // CTA-pair kernel (256x256 tiles, staged bf16 epilogue): when the problem fills the 74 SM pairs at least as well as
   // the single-CTA tiling fills the 148 SMs
   if (p.staged_ok && gemm_mode() != 1) {

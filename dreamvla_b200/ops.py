@@ -74,6 +74,22 @@ def _accum_bias_grad(param, dy2d):
     return tmp.to(torch.bfloat16)
 
 
+# Function.forward always runs with grad mode off, and ctx.needs_input_grad reports requires_grad of the inputs even under
+# torch.no_grad() (frozen ViT / CLIP towers, inference).  The wrappers record the caller's grad mode here so that forward
+# only writes and saves backward state (pre-activations, LN stats, LSE) when a backward can actually happen.
+_grad_on = True
+
+
+def _apply(fn, *args):
+    global _grad_on
+    prev = _grad_on
+    _grad_on = torch.is_grad_enabled()
+    try:
+        return fn.apply(*args)
+    finally:
+        _grad_on = prev
+
+
 class _Linear(torch.autograd.Function):
     """y = dropout(act(x @ W^T + b)) + residual.   weight_kn=False: W is [out,in] (nn.Linear); True: [in,out] (HF Conv1D)."""
 
@@ -81,7 +97,7 @@ class _Linear(torch.autograd.Function):
     def forward(ctx, x, weight, bias, residual, act, weight_kn, dropout_p, alpha):
         x2 = _as2d(_bf16c(x))
         N = weight.shape[1] if weight_kn else weight.shape[0]
-        need_grad = any(ctx.needs_input_grad)      # (Function.forward runs with grad mode off; this is the signal)
+        need_grad = _grad_on and any(ctx.needs_input_grad)
         aux = None
         if act != 0 and need_grad:
             aux = torch.empty((x2.shape[0], N), device=x2.device, dtype=torch.bfloat16)
@@ -126,7 +142,7 @@ class _Linear(torch.autograd.Function):
 
 def linear(x, weight, bias=None, *, act=None, residual=None, weight_kn=False, dropout_p=0.0, alpha=1.0):
     """Fused linear layer on the tcgen05 GEMM.  x [..., K] bf16."""
-    return _Linear.apply(x, weight, bias, residual, ACT_IDS[act] if not isinstance(act, int) else act, weight_kn,
+    return _apply(_Linear, x, weight, bias, residual, ACT_IDS[act] if not isinstance(act, int) else act, weight_kn,
                          float(dropout_p), float(alpha))
 
 
@@ -137,7 +153,7 @@ class _MLP(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, residual, act, weight_kn, dropout_p):
         x2 = _as2d(_bf16c(x))
-        need = any(ctx.needs_input_grad)
+        need = _grad_on and any(ctx.needs_input_grad)
         H = w1.shape[1] if weight_kn else w1.shape[0]
         N = w2.shape[1] if weight_kn else w2.shape[0]
         aux = torch.empty((x2.shape[0], H), device=x2.device, dtype=torch.bfloat16) if need else None
@@ -180,7 +196,7 @@ class _MLP(torch.autograd.Function):
 
 def mlp(x, w1, b1, w2, b2, *, act, residual=None, weight_kn=False, dropout_p=0.0):
     """Two-layer MLP block (timm Mlp / GPT2MLP / Perceiver FeedForward) on two fused-epilogue GEMMs."""
-    return _MLP.apply(x, w1, b1, w2, b2, residual, ACT_IDS[act] if not isinstance(act, int) else act, weight_kn,
+    return _apply(_MLP, x, w1, b1, w2, b2, residual, ACT_IDS[act] if not isinstance(act, int) else act, weight_kn,
                       float(dropout_p))
 
 
@@ -188,7 +204,7 @@ class _LayerNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, eps):
         x2 = _as2d(_bf16c(x))
-        need = any(ctx.needs_input_grad)
+        need = _grad_on and any(ctx.needs_input_grad)
         y, mean, rstd = L.layernorm_fwd(x2, gamma, beta, eps, save_stats=need)
         if need:
             ctx.save_for_backward(x2, mean, rstd)
@@ -219,7 +235,7 @@ class _LayerNorm(torch.autograd.Function):
 
 
 def layer_norm(x, gamma, beta, eps=1e-5):
-    return _LayerNorm.apply(x, gamma, beta, float(eps))
+    return _apply(_LayerNorm, x, gamma, beta, float(eps))
 
 
 class AttnMask:
@@ -256,7 +272,7 @@ class AttnMask:
 class _Attention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, scale, mask, dropout_p):
-        need = any(ctx.needs_input_grad)
+        need = _grad_on and any(ctx.needs_input_grad)
         seed = next_seed() if dropout_p > 0 else 0
         bits = mask.bits if mask is not None else None
         flags = mask.flags if mask is not None else None
@@ -293,7 +309,7 @@ class _Attention(torch.autograd.Function):
 
 def attention(q, k, v, scale, mask: AttnMask | None = None, dropout_p: float = 0.0):
     """q [B,Lq,H,64], k/v [B,Lk,H,64] (strided views allowed) -> [B,Lq,H,64] contiguous."""
-    return _Attention.apply(q, k, v, float(scale), mask, float(dropout_p))
+    return _apply(_Attention, q, k, v, float(scale), mask, float(dropout_p))
 
 
 class _FusedQKVAttention(torch.autograd.Function):
@@ -301,7 +317,7 @@ class _FusedQKVAttention(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, qkv, scale, mask, dropout_p):
-        need = any(ctx.needs_input_grad)
+        need = _grad_on and any(ctx.needs_input_grad)
         seed = next_seed() if dropout_p > 0 else 0
         q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
         o, lse = L.attn_fwd(q, k, v, scale, mask.bits if mask is not None else None,
@@ -328,7 +344,7 @@ class _FusedQKVAttention(torch.autograd.Function):
 def self_attention_fused(qkv, scale, mask: AttnMask | None = None, dropout_p: float = 0.0):
     """qkv [B, L, 3, H, 64] contiguous bf16 -> [B, L, H, 64]."""
     assert qkv.dim() == 5 and qkv.shape[2] == 3 and qkv.shape[4] == 64 and qkv.is_contiguous()
-    return _FusedQKVAttention.apply(qkv, float(scale), mask, float(dropout_p))
+    return _apply(_FusedQKVAttention, qkv, float(scale), mask, float(dropout_p))
 
 
 class _Dropout(torch.autograd.Function):
@@ -347,7 +363,7 @@ class _Dropout(torch.autograd.Function):
 def dropout(x, p: float, training: bool = True):
     if not training or p <= 0:
         return x
-    return _Dropout.apply(x, float(p))
+    return _apply(_Dropout, x, float(p))
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -70,6 +70,37 @@ def gemm_case(M, N, K, a_mn, b_mn, seed=0, timeit=False):
     report(f"gemm M{M} N{N} K{K} a_mn={int(a_mn)} b_mn={int(b_mn)}", rel(out, ref), 6e-3, extra)
 
 
+def gemm_accum_case(M, N, K, seed=0, timeit=True):
+    """weight-gradient form: G[M,N] += A[K,M]^T . B[K,N] (both operands MN-major), split-K eligible"""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    a = (torch.randn(K, M, generator=g) * 0.5).to(dev, torch.bfloat16)
+    b = (torch.randn(K, N, generator=g) * 0.5).to(dev, torch.bfloat16)
+    G0 = (torch.randn(M, N, generator=g) * 4.0).to(dev, torch.bfloat16)
+    ref = G0.float() + a.float().t() @ b.float()
+    G = G0.clone()
+    L.gemm(a, b, a_mn=True, b_mn=True, out=G, residual=G)
+    torch.cuda.synchronize()
+    extra = ""
+    if timeit:
+        scratch = torch.zeros_like(G)
+        ms = bench(lambda: L.gemm(a, b, a_mn=True, b_mn=True, out=scratch, residual=scratch, alpha=1e-3))
+        extra = f"{ms*1e3:.1f}us {2*M*N*K/ms/1e9:.0f} TFLOP/s"
+    report(f"gemm accumulate (wgrad) M{M} N{N} K{K}", rel(G, ref), 6e-3, extra)
+
+
+def group_gemm_splitk():
+    gemm_accum_case(1024, 1024, 10320)
+    gemm_accum_case(1024, 1024, 42400)
+    gemm_accum_case(1024, 3072, 10320)
+    gemm_accum_case(3072, 1024, 10320)
+    gemm_accum_case(1024, 768, 10320)
+    gemm_accum_case(768, 768, 31520)
+    gemm_accum_case(768, 3072, 31520)
+    gemm_accum_case(2304, 768, 31520)
+    gemm_accum_case(520, 264, 4104)      # tails in M, N and K with splits
+    gemm_accum_case(128, 136, 2048 + 8)
+
+
 def group_gemm_basic():
     for a_mn in (False, True):
         for b_mn in (False, True):
@@ -213,7 +244,7 @@ def pack_mask(mask_bool):
     return bits.to(dev)
 
 
-def attn_case(B, H, Lq, Lk, masked, fused_qkv=False, seed=3, timeit=False):
+def attn_case(B, H, Lq, Lk, masked, fused_qkv=False, seed=3, timeit=False, ramp=0.0):
     g = torch.Generator(device="cpu").manual_seed(seed)
     if fused_qkv:
         assert Lq == Lk
@@ -223,6 +254,9 @@ def attn_case(B, H, Lq, Lk, masked, fused_qkv=False, seed=3, timeit=False):
         q = torch.randn(B, Lq, H, 64, generator=g).to(dev, torch.bfloat16)
         k = torch.randn(B, Lk, H, 64, generator=g).to(dev, torch.bfloat16)
         v = torch.randn(B, Lk, H, 64, generator=g).to(dev, torch.bfloat16)
+        if ramp:      # key norms grow along the sequence: the running row max keeps rising (online-softmax rescale path)
+            k = (k.float() * (1.0 + ramp * torch.arange(Lk, device=dev).view(1, Lk, 1, 1) / Lk)).to(torch.bfloat16)
+            q = (q.float() * 2.0).to(torch.bfloat16)
     mask_bool = bits = flags = bits_t = None
     if masked:
         mask_bool = torch.rand(Lq, Lk, generator=g) < 0.3
@@ -238,7 +272,7 @@ def attn_case(B, H, Lq, Lk, masked, fused_qkv=False, seed=3, timeit=False):
     o, lse = L.attn_fwd(q, k, v, scale, bits, flags)
     qr, kr, vr = (t.detach().float().requires_grad_(True) for t in (q, k, v))
     oref = attn_ref(qr, kr, vr, scale, mask_bool)
-    tag = f"attn B{B} H{H} Lq{Lq} Lk{Lk} mask={int(masked)} fused={int(fused_qkv)}"
+    tag = f"attn B{B} H{H} Lq{Lq} Lk{Lk} mask={int(masked)} fused={int(fused_qkv)}" + (f" ramp={ramp}" if ramp else "")
     extra = ""
     if timeit:
         ms = bench(lambda: L.attn_fwd(q, k, v, scale, bits, flags))
@@ -270,6 +304,8 @@ def group_attn():
     attn_case(1, 2, 6, 6, False)
     attn_case(1, 2, 265, 265, True)
     attn_case(1, 2, 258, 258, True, fused_qkv=True)
+    attn_case(1, 2, 300, 520, False, ramp=6.0)
+    attn_case(2, 2, 515, 700, True, ramp=4.0)
     attn_case(2, 16, 1290, 1290, True, fused_qkv=True, timeit=True)
     attn_case(40, 12, 197, 197, False, fused_qkv=True, timeit=True)
     attn_case(40, 16, 265, 265, False, fused_qkv=True, timeit=True)
@@ -290,6 +326,43 @@ def group_attn():
     lhs = dv.float()[..., 0].sum(1)   # [B,H]
     rhs = o.float()[..., 0].sum(1)
     report("attn dropout bwd mask == fwd mask", rel(lhs, rhs), 5e-3)
+
+
+def group_attn_perf():
+    """fwd / bwd timings on the path's real attention shapes at per-GPU batch 8 (S = 10), real GPT-2 block mask"""
+    from dreamvla_b200 import ops
+    from dreamvla_b200.models.dreamvla_model import generate_attention_mask
+    g = torch.Generator(device="cpu").manual_seed(11)
+
+    def run(tag, B, H, L, mask=None, p=0.0):
+        qkv = torch.randn(B, L, 3, H, 64, generator=g).to(dev, torch.bfloat16)
+        q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+        bits = flags = bits_t = None
+        if mask is not None:
+            bits, bits_t, flags = mask.bits, mask.bits_t, mask.flags
+        o, lse = L_.attn_fwd(q, k, v, 0.125, bits, flags, dropout_p=p, dropout_seed=5)
+        d_o = torch.randn(B, L, H, 64, generator=g).to(dev, torch.bfloat16)
+        dqkv = torch.empty_like(qkv)
+        f = bench(lambda: L_.attn_fwd(q, k, v, 0.125, bits, flags, dropout_p=p, dropout_seed=5))
+        bw = bench(lambda: L_.attn_bwd(q, k, v, o, d_o, lse, 0.125, dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], bits, flags,
+                                       mask_bits_t=bits_t, dropout_p=p, dropout_seed=5))
+        vis = float(L * L) if mask is None else float(mask.visible)
+        gf = 4 * 64 * vis * B * H / 1e9
+        print(f"INFO attn_perf {tag:28s} fwd {f*1e3:7.1f} us ({gf/f:6.0f} TF/s)  bwd {bw*1e3:7.1f} us ({2.5*gf/bw:6.0f} TF/s)", flush=True)
+
+    L_ = L
+    run("vit B160 H12 L197", 160, 12, 197)
+    run("decoder B160 H16 L265", 160, 16, 265)
+    run("decoder B160 H16 L205", 160, 16, 205)
+    add = generate_attention_mask(K=10, num_A=36, num_B=93, atten_goal=0, atten_goal_state=False, atten_only_obs=False,
+                                  attn_robot_proprio_state=False, mask_l_obs_ratio=0.0, num_obs_token=90, action_pred_steps=3)
+    mb = (add == 0)
+    if mb is not None:
+        am = ops.AttnMask(mb, dev)
+        am.visible = int(mb.sum().item())
+        run("gpt2 B8 H16 L1290 mask", 8, 16, mb.shape[0], am)
+        run("gpt2 B8 H16 L1290 mask drop", 8, 16, mb.shape[0], am, p=0.1)
+    report("attn_perf ran", 0.0, 1.0)
 
 
 def group_loss():
@@ -359,8 +432,8 @@ def group_loss():
     report("adamw 3 steps (bf16 param rounding)", rel(Pc, pref.detach()), 8e-3)
 
 
-GROUPS = {"gemm_basic": group_gemm_basic, "gemm_big": group_gemm_big, "gemm_epilogue": group_gemm_epilogue,
-          "norm": group_norm, "attn": group_attn, "loss": group_loss}
+GROUPS = {"gemm_basic": group_gemm_basic, "gemm_splitk": group_gemm_splitk, "gemm_big": group_gemm_big, "gemm_epilogue": group_gemm_epilogue,
+          "norm": group_norm, "attn": group_attn, "attn_perf": group_attn_perf, "loss": group_loss}
 
 if __name__ == "__main__":
     grp = sys.argv[1]

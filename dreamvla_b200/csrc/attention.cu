@@ -32,6 +32,7 @@ struct AttnParams {
   const uint32_t* mask;
   const uint8_t* tile_flags;
   int B, H, Lq, Lk, nqt, nkt, mask_words;
+  int qt0, kt0;          // first q / kv 64-row tile of this launch (tail launches next to the tcgen05 kernels)
   long long q_sb, q_ss, q_sh, k_sb, k_ss, k_sh, v_sb, v_ss, v_sh, o_sb, o_ss, o_sh;
   long long do_sb, do_ss, do_sh, dq_sb, dq_ss, dq_sh, dk_sb, dk_ss, dk_sh, dv_sb, dv_ss, dv_sh;
   float scale;
@@ -184,7 +185,7 @@ __device__ __forceinline__ void dropout_bits(const AttnParams& p, long long bh, 
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
   __shared__ __align__(1024) uint8_t sm[5 * 8192];
   const uint32_t sQ = smem_u32(sm), sK0 = sQ + 8192, sV0 = sQ + 2 * 8192, sK1 = sQ + 3 * 8192, sV1 = sQ + 4 * 8192;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int qt = blockIdx.x + p.qt0, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
   const int q0 = qt * 64;
   const bf16* qg = p.q + b * p.q_sb + h * p.q_sh;
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnParams p) {
   __shared__ float s_lse[64], s_delta[64];
   __shared__ uint32_t s_mask[64][2];
   const uint32_t sK = smem_u32(sm), sV = sK + 8192, sQ = sK + 2 * 8192, sDO = sK + 3 * 8192;
-  const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int kt = blockIdx.x + p.kt0, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
   const int k0 = kt * 64;
   const bf16* qg = p.q + b * p.q_sb + h * p.q_sh;
@@ -452,7 +453,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnParams p) {
 __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnParams p) {
   __shared__ __align__(1024) uint8_t sm[4 * 8192];
   const uint32_t sQ = smem_u32(sm), sDO = sQ + 8192, sK = sQ + 2 * 8192, sV = sQ + 3 * 8192;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int qt = blockIdx.x + p.qt0, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
   const int q0 = qt * 64;
   const bf16* qg = p.q + b * p.q_sb + h * p.q_sh;
@@ -581,9 +582,10 @@ static bool strides_ok(const void* ptr, long long sb, long long ss, long long sh
 }
 
 int attn_fwd_tc_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s);   // attention_tc.cu (tcgen05 / TMEM, single-role CTA)
-int attn_fwd_ws_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s);   // attention_fwd_ws.cu (tcgen05, warp-specialised)
+int attn_fwd_ws_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s, long long q_rows);   // attention_fwd_ws.cu (tcgen05, warp-specialised)
 
-// 0 = auto (tcgen05 kernel for Lq >= 96, mma.sync kernel for short query blocks), 1 = force mma.sync, 2 = force tcgen05
+// 0 = auto (warp-specialised tcgen05 kernel for Lq >= 96, mma.sync kernel for short query blocks), 1 = mma.sync,
+// 2 = single-role tcgen05 kernel (attention_tc.cu), 3 = warp-specialised tcgen05 kernel whenever expressible
 static int attn_fwd_mode() {
   static int mode = -1;
   if (mode < 0) {
@@ -609,10 +611,6 @@ int attn_fwd_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s) {
     const int rc = attn_fwd_tc_dispatch(a, s);
     if (rc != DVLA_ERR_UNSUPPORTED) return rc;      // strides a tensor map cannot express -> mma.sync kernel below
   }
-  if (mode == 3) {
-    const int rc = attn_fwd_ws_dispatch(a, s);
-    if (rc != DVLA_ERR_UNSUPPORTED) return rc;
-  }
   AttnParams p;
   memset(&p, 0, sizeof(p));
   p.q = (const bf16*)a->q; p.k = (const bf16*)a->k; p.v = (const bf16*)a->v; p.out = (bf16*)a->o; p.lse = a->lse;
@@ -628,6 +626,12 @@ int attn_fwd_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s) {
     p.drop_seed = a->dropout_seed;
     p.drop_seed_ptr = a->dropout_seed_ptr;
   }
+  if (mode == 3 || (mode == 0 && a->Lq >= 96)) {
+    // warp-specialised tcgen05 kernel on 256-query CTAs.  (Sending a short remainder of <= 64 rows to the mma.sync kernel
+    // instead of a latency-bound CTA was measured and lost: profiles/r1_notes.md.)
+    const int rc = attn_fwd_ws_dispatch(a, s, a->Lq);
+    if (rc != DVLA_ERR_UNSUPPORTED) return rc;
+  }
   attn_fwd_kernel<<<dim3(p.nqt, p.H, p.B), 128, 0, s>>>(p);
   DVLA_CHECK_LAUNCH("attn_fwd");
   return DVLA_OK;
@@ -635,9 +639,11 @@ int attn_fwd_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s) {
 
 int attn_bwd_tc_dispatch(const dvla_attn_bwd_args* a, const uint32_t* mask_t, int mask_t_words, cudaStream_t s);  // attention_bwd_tc.cu
 int attn_bwd_pipe_dispatch(const dvla_attn_bwd_args* a, const uint32_t* mask_t, int mask_t_words, cudaStream_t s);  // attention_bwd_pipe.cu
-int attn_bwd_ws_dispatch(const dvla_attn_bwd_args* a, const uint32_t* mask_t, int mask_t_words, cudaStream_t s);    // attention_bwd_ws.cu
+int attn_bwd_ws_dispatch(const dvla_attn_bwd_args* a, const uint32_t* mask_t, int mask_t_words, cudaStream_t s, long long q_rows,
+                         long long k_rows);    // attention_bwd_ws.cu
 
-// 0 = auto (tcgen05 kernels when both sequences are >= 96 long), 1 = force mma.sync, 2 = force tcgen05
+// 0 = auto (warp-specialised tcgen05 kernels when both sequences are >= 96 long), 1 = mma.sync kernels,
+// 2 = single-role tcgen05 kernels (attention_bwd_tc.cu), 3 = attention_bwd_pipe.cu, 4 = warp-specialised whenever expressible
 static int attn_bwd_mode() {
   static int mode = -1;
   if (mode < 0) {
@@ -687,11 +693,12 @@ int attn_bwd_dispatch(const dvla_attn_bwd_args* a, cudaStream_t s) {
     const int rc = attn_bwd_pipe_dispatch(a, a->mask_t, a->mask_t_words, s);
     if (rc != DVLA_ERR_UNSUPPORTED) return rc;
   }
-  if (bmode == 4) {      // warp-specialised tcgen05 kernels, 2 CTAs / SM (attention_bwd_ws.cu)
-    const int rc = attn_bwd_ws_dispatch(a, a->mask_t, a->mask_t_words, s);
+  if (bmode == 4 || (bmode == 0 && a->Lq >= 96 && a->Lk >= 96)) {
+    // warp-specialised tcgen05 kernels, 2 CTAs / SM (attention_bwd_ws.cu)
+    const int rc = attn_bwd_ws_dispatch(a, a->mask_t, a->mask_t_words, s, a->Lq, a->Lk);
     if (rc != DVLA_ERR_UNSUPPORTED) return rc;
   }
-  if (bmode == 2 || (bmode == 0 && a->Lq >= 96 && a->Lk >= 96)) {
+  if (bmode == 2) {
     const int rc = attn_bwd_tc_dispatch(a, a->mask_t, a->mask_t_words, s);
     if (rc != DVLA_ERR_UNSUPPORTED) return rc;
   }

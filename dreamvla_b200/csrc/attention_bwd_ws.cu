@@ -475,7 +475,8 @@ bool make_attn_tmap_rows(CUtensorMap* out, const void* base, long long L, long l
                          long long sh, long long sb, int box_rows, int* head_inner);   // attention_fwd_ws.cu
 
 // DVLA_ERR_UNSUPPORTED -> caller uses another backward
-int attn_bwd_ws_dispatch(const dvla_attn_bwd_args* a, const uint32_t* mask_t, int mask_t_words, cudaStream_t s) {
+int attn_bwd_ws_dispatch(const dvla_attn_bwd_args* a, const uint32_t* mask_t, int mask_t_words, cudaStream_t s, long long q_rows,
+                         long long k_rows) {   // q_rows / k_rows: Lq / Lk, or a multiple of 128 below (the caller covers the rest)
   auto okst = [&](long long ss, long long sh, long long sb) {
     return ss > 0 && sh > 0 && (a->B == 1 || sb > 0) && ss % 8 == 0 && sh % 8 == 0 && sb % 8 == 0;
   };
@@ -504,6 +505,8 @@ int attn_bwd_ws_dispatch(const dvla_attn_bwd_args* a, const uint32_t* mask_t, in
     cudaError_t e1 = cudaFuncSetAttribute(attn_bwd_dkv_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_DKV_WS_SMEM);
     cudaError_t e2 = cudaFuncSetAttribute(attn_bwd_dq_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_DQ_WS_SMEM);
     if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("attn_bwd_ws smem attr failed"); return DVLA_ERR_CUDA; }
+    cudaFuncSetAttribute(attn_bwd_dkv_ws_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   // 2 CTAs / SM
+    cudaFuncSetAttribute(attn_bwd_dq_ws_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     attr_set = true;
   }
   CUtensorMap q64, do64, k128, v128, q128, do128, k64, v64;
@@ -516,12 +519,12 @@ int attn_bwd_ws_dispatch(const dvla_attn_bwd_args* a, const uint32_t* mask_t, in
   if (!make_attn_tmap_rows(&do128, a->d_o, a->Lq, a->H, a->B, a->do_ss, a->do_sh, a->do_sb, 128, &hi)) return DVLA_ERR_CUDA;
   if (!make_attn_tmap_rows(&k64, a->k, a->Lk, a->H, a->B, a->k_ss, a->k_sh, a->k_sb, 64, &hi)) return DVLA_ERR_CUDA;
   if (!make_attn_tmap_rows(&v64, a->v, a->Lk, a->H, a->B, a->v_ss, a->v_sh, a->v_sb, 64, &hi)) return DVLA_ERR_CUDA;
-  dim3 gkv((unsigned)((a->Lk + 127) / 128), (unsigned)a->H, (unsigned)a->B);
+  dim3 gkv((unsigned)((k_rows + 127) / 128), (unsigned)a->H, (unsigned)a->B);
   attn_bwd_dkv_ws_kernel<<<gkv, BW_THREADS, ATTN_DKV_WS_SMEM, s>>>(q64, k128, v128, do64, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("attn_bwd_dkv_ws launch: %s", cudaGetErrorString(e)); return DVLA_ERR_CUDA; }
   count_launch();
-  dim3 gq((unsigned)((a->Lq + 127) / 128), (unsigned)a->H, (unsigned)a->B);
+  dim3 gq((unsigned)((q_rows + 127) / 128), (unsigned)a->H, (unsigned)a->B);
   attn_bwd_dq_ws_kernel<<<gq, BW_THREADS, ATTN_DQ_WS_SMEM, s>>>(q128, k64, v64, do128, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("attn_bwd_dq_ws launch: %s", cudaGetErrorString(e)); return DVLA_ERR_CUDA; }

@@ -16,6 +16,8 @@
 // the probabilities (HF GPT2Attention._attn / timm Attention.forward).
 #include "common.cuh"
 #include "../../include/dvla.h"
+#include <stdlib.h>
+#include <string.h>
 
 namespace dvla {
 void set_error(const char* fmt, ...);
@@ -46,6 +48,7 @@ struct AttnWsParams {
   int q_head_inner, k_head_inner, v_head_inner;
   float scale;
   float drop_scale; uint32_t drop_thresh; uint64_t drop_seed; const uint64_t* drop_seed_ptr;
+  int trace;                   // DVLA_ATTN_TRACE=1: event timestamps (cycles since CTA start) overwrite the LSE rows of q-tile 0
 };
 
 __device__ __forceinline__ void tma_load_4d_ws(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -131,6 +134,16 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+#ifdef DVLA_ATTN_TRACE_BUILD      // build with -DDVLA_ATTN_TRACE_BUILD and run with DVLA_ATTN_TRACE=1 (tools/attn_trace.py)
+  const long long t_start = clock64();
+  float* trace_base = (p.trace && p.lse && qt == 0) ? p.lse + (static_cast<long long>(b) * p.H + h) * p.Lq : nullptr;
+  auto trace = [&](int slot) {
+    if (trace_base && slot < 256 && slot < p.Lq) trace_base[slot] = static_cast<float>(clock64() - t_start);
+  };
+#else
+  constexpr float* trace_base = nullptr;
+  auto trace = [](int) {};
+#endif
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer ------------------------------------------------
@@ -163,6 +176,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           if (sflag[t * WS_MAX_KT + j] == 0) continue;
           mbar_wait(&p_ready[t], cp[t] & 1);
           tc_fence_after();
+          trace(4 + cp[t] * 6 + t);
           const uint32_t pa = smem_u32(smem + SM_P + t * 16384);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -174,11 +188,13 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         umma_commit(&kv_free[st]);
       };
       mbar_wait(q_full, 0);
+      trace(0);
       for (int j = 0; j < nkt; ++j) {
         if ((sflag[j] | sflag[WS_MAX_KT + j]) == 0) continue;
         const int st = idx % WS_STAGES;
         mbar_wait(&kv_full[st], (idx / WS_STAGES) & 1);
         tc_fence_after();
+        trace(1 + idx * 6);
         const uint32_t ka = smem_u32(smem + SM_KV + st * 16384);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
@@ -191,6 +207,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                          make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
           umma_commit(&s_full[t]);
           ++cs[t];
+          trace(2 + idx * 6 + t);
         }
         if (prev_j >= 0) issue_pv(prev_j, prev_st);
         prev_j = j; prev_st = st; ++idx;
@@ -234,8 +251,13 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             w1 &= rem <= 32 ? 0u : ((1u << (rem - 32)) - 1u);
           }
         }
+        const bool tr = (quarter == 2) && lane == 0;
+        const int tb = 64 + t * 64 + c * 10;
+        if (tr) trace(tb);
         mbar_wait(&s_full[t], c & 1);
+        if (tr) trace(tb + 1);
         tc_fence_after();
+        if (tr) trace(tb + 2);
         float factor = 1.f;
         bool need = false;
         uint32_t pk[32];
@@ -252,9 +274,11 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
             for (int i = 0; i < 32; ++i) { s[i] = __uint_as_float(r0[i]); s[32 + i] = __uint_as_float(r1[i]); }
           }
+          if (tr) trace(tb + 3);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&s_free[t]);
+          if (tr) trace(tb + 4);
           float tmax = -INFINITY;
           if (f == 2) {
 #pragma unroll
@@ -295,9 +319,12 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
           l_run += lsum;
         }
+        if (tr) trace(tb + 5);
         if (c > 0) {
           mbar_wait(&pv_done[t], (c - 1) & 1);        // P buffer free, O_t quiescent
+          if (tr) trace(tb + 6);
           tc_fence_after();
+          if (tr) trace(tb + 7);
           if (__any_sync(0xffffffffu, need)) {          // rare: the row max grew by more than 2^8 -> rescale O
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
@@ -317,7 +344,9 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             *reinterpret_cast<uint4*>(prow + ((g ^ (r_in & 7)) << 4)) =
                 make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
         }
+        if (tr) trace(tb + 8);
         fence_proxy_async_smem();
+        if (tr) trace(tb + 9);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_ready[t]);
@@ -328,6 +357,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_wait(&pv_done[t], (c - 1) & 1);
         tc_fence_after();
       }
+      if (quarter == 2 && lane == 0) trace(64 + t * 64 + 60);
       if (warp_active) {
         const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
         bf16* dst = p.out + b * p.o_sb + static_cast<long long>(row) * p.o_ss + h * p.o_sh;
@@ -351,7 +381,8 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                              pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv));
           }
         }
-        if (p.lse && row < p.Lq) p.lse[bh * p.Lq + row] = (l_run > 0.f) ? (m_ref + log2f(l_run)) * WS_LN2 : -INFINITY;
+        if (quarter == 2 && lane == 0) trace(64 + t * 64 + 61);
+        if (p.lse && row < p.Lq && !trace_base) p.lse[bh * p.Lq + row] = (l_run > 0.f) ? (m_ref + log2f(l_run)) * WS_LN2 : -INFINITY;
       }
     }
   }
@@ -394,7 +425,7 @@ bool make_attn_tmap_rows(CUtensorMap* out, const void* base, long long L, long l
 
 // returns DVLA_OK, or DVLA_ERR_UNSUPPORTED when the strides cannot be expressed as a tensor map or Lk is too long for the
 // per-CTA flag table (the caller then takes the mma.sync forward kernel, which has no such restriction)
-int attn_fwd_ws_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s) {
+int attn_fwd_ws_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s, long long q_rows) {
   auto ok_strides = [](long long ss, long long sh, long long sb, long long B) {
     return ss > 0 && sh > 0 && (B == 1 || sb > 0) && ss % 8 == 0 && sh % 8 == 0 && sb % 8 == 0;
   };
@@ -418,6 +449,7 @@ int attn_fwd_ws_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s) {
   p.nkt = nkt; p.mask_words = a->mask_words;
   p.o_sb = a->o_sb; p.o_ss = a->o_ss; p.o_sh = a->o_sh;
   p.scale = a->scale;
+  { static int tr = -1; if (tr < 0) { const char* e = getenv("DVLA_ATTN_TRACE"); tr = (e && e[0] == '1') ? 1 : 0; } p.trace = tr; }
   if (a->dropout_p > 0.f) {
     p.drop_thresh = (uint32_t)(a->dropout_p * 65536.0f + 0.5f);
     p.drop_scale = 1.0f / (1.0f - (float)p.drop_thresh / 65536.0f);
@@ -428,9 +460,10 @@ int attn_fwd_ws_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s) {
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM);
     if (e != cudaSuccess) { set_error("attn_fwd_ws smem attr: %s", cudaGetErrorString(e)); return DVLA_ERR_CUDA; }
+    cudaFuncSetAttribute(attn_fwd_ws_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   // room for 2 CTAs / SM
     attr_set = true;
   }
-  dim3 grid((unsigned)((a->Lq + 255) / 256), (unsigned)a->H, (unsigned)a->B);
+  dim3 grid((unsigned)((q_rows + 255) / 256), (unsigned)a->H, (unsigned)a->B);   // q_rows: Lq, or a multiple of 256 below it
   attn_fwd_ws_kernel<<<grid, WS_THREADS, WS_SMEM, s>>>(tmQ, tmK, tmV, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("attn_fwd_ws launch: %s", cudaGetErrorString(e)); return DVLA_ERR_CUDA; }

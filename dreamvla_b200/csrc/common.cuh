@@ -52,11 +52,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+  uint32_t spins = 0;
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > DVLA_WATCHDOG_CYCLES) {
-      printf("dvla: mbarrier watchdog (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
-      __trap();
+    if ((++spins & 0x3FFu) == 0) {                  // watchdog: look at the clock only every 1024 failed polls
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > DVLA_WATCHDOG_CYCLES) {
+        printf("dvla: mbarrier watchdog (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+        __trap();
+      }
     }
   }
 }

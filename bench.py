@@ -147,8 +147,15 @@ def run_ours(args):
             raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    verbose = bool(os.environ.get("DVLA_BENCH_VERBOSE"))
+    t_begin = time.perf_counter()
+
+    def stage(msg):
+        if verbose:
+            print(f"[bench r{rank} +{time.perf_counter() - t_begin:6.1f}s] {msg}", file=sys.stderr, flush=True)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    stage("process group up")
     cfg = CONFIGS[args.config]
     scfg = StepConfig(**cfg["step"])
     model = build_model(cfg, dev, args.dropout, args.layers)
@@ -167,11 +174,13 @@ def run_ours(args):
 
     eager_step = step
     graphed = False
+    stage("model + batch built")
     if not args.no_graph:
         try:
             step = GraphedTrainStep(eager_step, batch, warmup=3)
             batch = step.static
             graphed = True
+            stage("graphs captured")
         except Exception as e:  # noqa: BLE001  (same kernels either way; only the launch mechanism differs)
             print(f"[bench] CUDA-graph capture failed, launching eagerly: {e!r}", file=sys.stderr, flush=True)
             torch.cuda.synchronize()
@@ -181,6 +190,7 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         loss = step(batch)
     sync_all()
+    stage("warm-up done")
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -203,6 +213,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t)
+    stage("timed region done")
     ms_per_step = ms / args.steps
     value = B * world / (ms_per_step / 1e3)
     final_loss = float(loss)
@@ -270,6 +281,7 @@ def run_ours(args):
                 "step_model_tflops": round(cfg["tf_per_sample"] * B / (ms_per_step * 1e-3), 1),
                 "step_frac_of_peak": round(cfg["tf_per_sample"] * B / (ms_per_step * 1e-3) / peak, 4)}
 
+    stage("roofline done")
     # ---- end-to-end: pinned host inputs -> H2D -> step -> D2H loss, every step ----
     e2e = None
     if not args.no_e2e:
@@ -300,6 +312,7 @@ def run_ours(args):
         e2e = {"value": round(B * world / (e2e_ms / 1e3), 3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms, 3), "wall_ms_per_step": round(wall / args.steps, 3)}
 
+    stage("e2e done")
     cpu = None
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         cpu = cpu_baseline(args, steps=1, warm=0)
@@ -319,7 +332,10 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # tear-down: CUDA graphs that recorded NCCL kernels must die before the communicator
+        step = eager_step = None
+        from dreamvla_b200.utils.distributed_utils import shutdown_distributed
+        shutdown_distributed()
 
 
 # ----------------------------------------------------------------------------------------------------------------------

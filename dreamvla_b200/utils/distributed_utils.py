@@ -43,3 +43,29 @@ def init_distributed_device(args):
         args.distributed = True
     args.device = device
     return device
+
+
+def shutdown_distributed(timeout_s: float = 20.0):
+    """Orderly tear-down for one-process-per-GPU runs.  CUDA graphs that recorded NCCL kernels must be released before the
+    communicator: drop every reference to them before calling this.  destroy_process_group() is given `timeout_s`; if it
+    does not return (graphs still alive somewhere) the process leaves without it instead of hanging until the launcher's
+    timeout."""
+    import gc
+    import sys
+    import threading
+    dist = torch.distributed
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    dist.barrier()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    sys.stdout.flush()
+    th = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    th.start()
+    th.join(timeout=timeout_s)
+    if th.is_alive():
+        sys.stderr.flush()
+        os._exit(0)

@@ -167,4 +167,6 @@ def main(args, loader=None):
 
 
 if __name__ == "__main__":
-    main(get_parser().parse_args())
+    main(get_parser().parse_args())          # the returned state (and with it any captured graphs) is dropped here
+    from dreamvla_b200.utils.distributed_utils import shutdown_distributed
+    shutdown_distributed()

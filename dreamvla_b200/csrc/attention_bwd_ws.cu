@@ -180,6 +180,11 @@ attn_bwd_dq_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         if (lane == 0) mbar_arrive(sdp_free);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
+          if (f == 1 && ((wv >> (8 * g)) & 0xffu) == 0u) {      // 8 hidden keys: dS = 0 without exp2 / Philox
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pk[g * 4 + i] = 0u;
+            continue;
+          }
           uint32_t keep = 0xffu;
           if (has_drop) keep = dropout_keep8(seed, (bh * p.Lq + row) * nblk + (k0 >> 3) + g, p.drop_thresh);
           float ds[8];
@@ -397,16 +402,29 @@ attn_bwd_dkv_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         if (lane == 0) mbar_arrive(sdp_free);
         const float4* lse_t = reinterpret_cast<const float4*>(s_lse + st * 128 + half * 32);
         const float4* dl_t = reinterpret_cast<const float4*>(s_lse + st * 128 + 64 + half * 32);
+        // groups of 8 queries that no key row of this warp can see (block masks: most of them) are skipped warp-wide
+        uint32_t live = 0xfu;
+        if (f == 1) {
+          live = 0u;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) live |= __any_sync(0xffffffffu, ((wv >> (8 * g)) & 0xffu) != 0u) ? (1u << g) : 0u;
+        }
         uint32_t keepm[4] = {0, 0, 0, 0};           // dropout: lane (key%8 == r) owns queries c == r (mod 8)
         if (has_drop) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
+            if (!((live >> g) & 1u)) continue;
             const long long qc = q0 + (lane & 7) + g * 8;
             keepm[g] = dropout_keep8(seed, (bh * p.Lq + qc) * nblk + (key >> 3), p.drop_thresh);
           }
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
+          if (!((live >> g) & 1u)) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { pkp[g * 4 + u] = 0u; pkd[g * 4 + u] = 0u; }
+            continue;
+          }
           float pv[8], ds[8];
 #pragma unroll
           for (int q4 = 0; q4 < 2; ++q4) {

@@ -303,6 +303,12 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const uint64_t blk0 = (static_cast<uint64_t>(bh) * p.Lq + row) * nblk + (k0 >> 3);
 #pragma unroll
           for (int g = 0; g < 8; ++g) {                  // 8 keys at a time: exp2, row sum, dropout, pack to bf16
+            if (f == 1 && (((g < 4 ? w0 >> (8 * g) : w1 >> (8 * (g - 4))) & 0xffu) == 0u)) {
+              // all 8 keys hidden from this row (block masks hide 60 % of the pairs inside partial tiles): no exp2, no Philox
+#pragma unroll
+              for (int i = 0; i < 4; ++i) pk[g * 4 + i] = 0u;
+              continue;
+            }
             float e[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {

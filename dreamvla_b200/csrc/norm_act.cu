@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
 // and one fp32 atomicAdd per column per CTA.
 // ------------------------------------------------------------------------------------------------------------------
 template <int NV>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                             const bf16* __restrict__ gamma, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, bf16* __restrict__ dx,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -109,32 +109,48 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
 #pragma unroll
     for (int j = 0; j < 8; ++j) { pg[i][j] = 0.f; pb[i][j] = 0.f; }
 
+  auto unpack8 = [](const uint4& u, float (&f)[8]) {
+    float2 t;
+    t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+    t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+    t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+    t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+  };
+  // The row is kept as the RAW bf16 vectors it was loaded as (8 registers per 16 B of x and dy instead of 16 fp32) and
+  // unpacked twice: with the dgamma/dbeta partials that fits 128 registers, i.e. two CTAs per SM and twice the loads in
+  // flight of this latency-bound, HBM-limited kernel.
   for (long long row = static_cast<long long>(blockIdx.x) * 8 + warp; row < rows; row += static_cast<long long>(gridDim.x) * 8) {
+    uint4 xr[NV], dr[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        xr[i] = __ldg(reinterpret_cast<const uint4*>(x + row * ld + vi * 8));
+        dr[i] = __ldg(reinterpret_cast<const uint4*>(dy + row * ld + vi * 8));
+      } else {
+        xr[i] = make_uint4(0, 0, 0, 0);
+        dr[i] = make_uint4(0, 0, 0, 0);
+      }
+    }
     const float mu = mean[row], rs = rstd[row];
-    float xh[NV][8], gdy[NV][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + i * 32;
       if (vi < nvec) {
         float xv[8], dv[8], gm[8];
-        load8(x + row * ld + vi * 8, xv);
-        load8(dy + row * ld + vi * 8, dv);
+        unpack8(xr[i], xv);
+        unpack8(dr[i], dv);
         if (gamma) load8(gamma + vi * 8, gm);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float h = (xv[j] - mu) * rs;
-          xh[i][j] = h;
           pg[i][j] += dv[j] * h;
           pb[i][j] += dv[j];
           const float gd = gamma ? dv[j] * gm[j] : dv[j];
-          gdy[i][j] = gd;
           s1 += gd;
           s2 += gd * h;
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { xh[i][j] = 0.f; gdy[i][j] = 0.f; }
       }
     }
     s1 = warp_sum(s1) / D;
@@ -143,9 +159,16 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + i * 32;
       if (vi < nvec) {
-        float o[8];
+        float xv[8], dv[8], gm[8], o[8];
+        unpack8(xr[i], xv);
+        unpack8(dr[i], dv);
+        if (gamma) load8(gamma + vi * 8, gm);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rs * (gdy[i][j] - s1 - xh[i][j] * s2);
+        for (int j = 0; j < 8; ++j) {
+          const float h = (xv[j] - mu) * rs;
+          const float gd = gamma ? dv[j] * gm[j] : dv[j];
+          o[j] = rs * (gd - s1 - h * s2);
+        }
         store8(dx + row * ld + vi * 8, o);
       }
     }
@@ -201,7 +224,7 @@ int layernorm_bwd_dispatch(const dvla_layernorm_bwd_args* a, cudaStream_t stream
   if (a->rows <= 0) return DVLA_OK;
   const int nv = (int)((a->D + 255) / 256);
   long long blocks = (a->rows + 7) / 8;
-  const long long cap = (long long)num_sms();   // fewer, longer-lived blocks: 2*D fp32 atomics per block at the end
+  const long long cap = 2LL * num_sms();        // 2 resident blocks per SM; 2*D fp32 atomics per block at the end
   if (blocks > cap) blocks = cap;
 #define LN_BWD(NV) layernorm_bwd_kernel<NV><<<(unsigned)blocks, 256, 0, stream>>>((const bf16*)a->dy, (const bf16*)a->x, \
       (const bf16*)a->gamma, a->mean, a->rstd, (bf16*)a->dx, a->dgamma, a->dbeta, a->rows, (int)a->D, a->ld)
@@ -226,7 +249,21 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
     const int col = blockIdx.x * 256 + lane * 8;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (col < N) {
-      for (long long r = r0 + warp; r < r1; r += 8) {
+      long long r = r0 + warp;
+      for (; r + 24 < r1; r += 32) {            // 4 independent 16-byte loads in flight per lane
+        uint4 u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(x + (r + 8 * k) * ld + col));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float2 t;
+          t = unpack_bf16x2(u[k].x); acc[0] += t.x; acc[1] += t.y;
+          t = unpack_bf16x2(u[k].y); acc[2] += t.x; acc[3] += t.y;
+          t = unpack_bf16x2(u[k].z); acc[4] += t.x; acc[5] += t.y;
+          t = unpack_bf16x2(u[k].w); acc[6] += t.x; acc[7] += t.y;
+        }
+      }
+      for (; r < r1; r += 8) {
         float f[8];
         load8(x + r * ld + col, f);
 #pragma unroll
@@ -256,8 +293,8 @@ int colsum_accum_dispatch(const void* x, int64_t rows, int64_t N, int64_t ld, fl
   if (rows <= 0 || N <= 0) return DVLA_OK;
   const int vec = (N % 8 == 0) && (ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   const int bx = (int)((N + 255) / 256);
-  int by = (int)((2LL * num_sms() + bx - 1) / bx);
-  if (by > (rows + 31) / 32) by = (int)((rows + 31) / 32);
+  int by = (int)((6LL * num_sms() + bx - 1) / bx);     // ~6 blocks of 256 threads per SM: enough loads in flight for HBM
+  if (by > (rows + 63) / 64) by = (int)((rows + 63) / 64);
   if (by < 1) by = 1;
   const int rpb = (int)((rows + by - 1) / by);
   by = (int)((rows + rpb - 1) / rpb);
@@ -328,8 +365,31 @@ int dropout_dispatch(const void* x, void* y, int64_t rows, int64_t N, int64_t ld
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void act_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ pre, bf16* __restrict__ dx,
-                               long long n, int act) {
+// dx = dy * act'(pre): HBM-bound (2 reads + 1 write of 2 B per element); 8 elements (16 B) per thread per access, the
+// activation switch hoisted out of the element loop (act_bwd_mul_n)
+__global__ void __launch_bounds__(256) act_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ pre,
+                                                      bf16* __restrict__ dx, long long n, int act) {
+  const long long nvec = n >> 3;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const uint4* dy4 = reinterpret_cast<const uint4*>(dy);
+  const uint4* pre4 = reinterpret_cast<const uint4*>(pre);
+  uint4* dx4 = reinterpret_cast<uint4*>(dx);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const uint4 a = __ldg(dy4 + i), b = __ldg(pre4 + i);
+    float v[8], x[8];
+    float2 f;
+    f = unpack_bf16x2(a.x); v[0] = f.x; v[1] = f.y; f = unpack_bf16x2(a.y); v[2] = f.x; v[3] = f.y;
+    f = unpack_bf16x2(a.z); v[4] = f.x; v[5] = f.y; f = unpack_bf16x2(a.w); v[6] = f.x; v[7] = f.y;
+    f = unpack_bf16x2(b.x); x[0] = f.x; x[1] = f.y; f = unpack_bf16x2(b.y); x[2] = f.x; x[3] = f.y;
+    f = unpack_bf16x2(b.z); x[4] = f.x; x[5] = f.y; f = unpack_bf16x2(b.w); x[6] = f.x; x[7] = f.y;
+    act_bwd_mul_n<8>(v, x, act);
+    dx4[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+  for (long long i = (nvec << 3) + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    dx[i] = __float2bfloat16(__bfloat162float(dy[i]) * act_bwd(__bfloat162float(pre[i]), act));
+}
+__global__ void act_bwd_scalar_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ pre, bf16* __restrict__ dx,
+                                      long long n, int act) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     dx[i] = __float2bfloat16(__bfloat162float(dy[i]) * act_bwd(__bfloat162float(pre[i]), act));
@@ -337,9 +397,11 @@ __global__ void act_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restri
 int act_bwd_dispatch(const void* dy, const void* pre, void* dx, int64_t n, int32_t act, cudaStream_t s) {
   if (!dy || !pre || !dx) { set_error("act_bwd: null pointer"); return DVLA_ERR_INVALID; }
   if (n <= 0) return DVLA_OK;
-  long long blocks = (n + 255) / 256;
+  const bool vec = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
+  long long blocks = ((vec ? (n + 7) / 8 : n) + 255) / 256;
   if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
-  act_bwd_kernel<<<(unsigned)blocks, 256, 0, s>>>((const bf16*)dy, (const bf16*)pre, (bf16*)dx, n, act);
+  if (vec) act_bwd_kernel<<<(unsigned)blocks, 256, 0, s>>>((const bf16*)dy, (const bf16*)pre, (bf16*)dx, n, act);
+  else     act_bwd_scalar_kernel<<<(unsigned)blocks, 256, 0, s>>>((const bf16*)dy, (const bf16*)pre, (bf16*)dx, n, act);
   DVLA_CHECK_LAUNCH("act_bwd");
   return DVLA_OK;
 }

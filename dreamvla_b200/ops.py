@@ -90,6 +90,17 @@ def _apply(fn, *args):
         _grad_on = prev
 
 
+def on_grad_ready(t: torch.Tensor, callback):
+    """Run `callback()` during backward at the moment the gradient w.r.t. `t` is complete, i.e. when every op that consumed
+    `t` (and everything downstream of it) has enqueued its backward kernels -- including the fused weight-gradient GEMMs.
+    The gradient itself is left untouched."""
+    def _hook(grad):
+        callback()
+        return None
+    t.register_hook(_hook)
+    return t
+
+
 class _Linear(torch.autograd.Function):
     """y = dropout(act(x @ W^T + b)) + residual.   weight_kn=False: W is [out,in] (nn.Linear); True: [in,out] (HF Conv1D)."""
 

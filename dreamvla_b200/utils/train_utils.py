@@ -15,6 +15,8 @@ Here:
 from __future__ import annotations
 
 import math
+import os
+import re
 import time
 from dataclasses import dataclass
 
@@ -36,6 +38,24 @@ HEAD_PREFIXES = {
     "sam": ("sam_feat_decoder", "sam_decoder", "sam_mask_token", "sam_feat_tokens"),
     "traj": ("traj_decoder", "traj_mask_token", "trajectory_tokens"),
 }
+
+
+# Parameters whose gradients are complete once the backward pass reaches the backbone output (decoders, heads, DiT): their
+# flat-buffer segment is all-reduced while the backbone is still back-propagating.  (The query tokens `obs_tokens`,
+# `*_tokens`, `action_pred_token` are INPUTS of the backbone: their gradients complete last.)
+EARLY_GRAD_PREFIXES = ("image_decoder", "mask_token", "depth_decoder", "depth_mask_token", "dino_feat_decoder", "dino_decoder",
+                       "dino_mask_token", "sam_feat_decoder", "sam_decoder", "sam_mask_token", "traj_decoder", "traj_mask_token",
+                       "action_model.", "action_decoder", "arm_action_decoder", "gripper_action_decoder")
+
+
+def grad_segment(name: str, n_layers: int) -> int:
+    """0: complete at the backbone output; 1: complete at the input of backbone layer n_layers//2; 2: complete at the end."""
+    if name.startswith(EARLY_GRAD_PREFIXES):
+        return 0
+    m = re.match(r"transformer_backbone\.h\.(\d+)\.", name)
+    if (m and int(m.group(1)) >= n_layers // 2) or name.startswith("transformer_backbone.ln_f."):
+        return 1
+    return 2
 
 
 def get_cast_dtype(precision: str):
@@ -163,6 +183,8 @@ class FlatParams:
             if p.dtype != torch.bfloat16 or not p.is_cuda:
                 raise RuntimeError(f"FlatParams: {name} is {p.dtype} on {p.device}; the train step is bf16/CUDA only")
             (small if p.dim() <= 1 else big).append((name, p))
+        n_layers = len(model.transformer_backbone.h)
+        big.sort(key=lambda np_: grad_segment(np_[0], n_layers))          # stable: registration order inside a segment
         self.params = big + small
         dev = self.params[0][1].device
 
@@ -175,6 +197,9 @@ class FlatParams:
             off += aligned(p.numel())
         self.n_big = sum(aligned(p.numel()) for _, p in big)
         self.n = off
+        # [0, seg_end[0]) and [seg_end[0], seg_end[1]) hold the >=2-D gradients of segments 0 / 1 (see grad_segment)
+        self.seg_end = [sum(aligned(p.numel()) for n_, p in big if grad_segment(n_, n_layers) <= k) for k in (0, 1)]
+        self.mid_layer = n_layers // 2
         self.P = torch.zeros(self.n, device=dev, dtype=torch.bfloat16)
         self.G = torch.zeros(self.n, device=dev, dtype=torch.bfloat16)
         self.G32 = torch.zeros(max(self.n - self.n_big, 8), device=dev, dtype=torch.float32)
@@ -321,6 +346,12 @@ class TrainStep:
         self.micro = 0
         self.comm_stream = torch.cuda.Stream() if world_size > 1 else None
         self.last_terms = {}
+        # EXPERIMENTAL (opt-in, DVLA_AR_OVERLAP=1): all-reduce the gradient segments that complete early from backward
+        # hooks so that the exchange overlaps the rest of the backward pass.  Round-1 status: the 2-GPU check
+        # (tools/ddp_overlap_check.py) did not pass and the captured variant hung, so the default remains ONE flat
+        # all-reduce on the communication stream after backward (validated on 2 GPUs, profiles/r1_bench_2gpu_b8.log).
+        self.overlap = world_size > 1 and os.environ.get("DVLA_AR_OVERLAP", "0") == "1"
+        self._reduced_upto = 0
 
     def prepare_inputs(self, batch):
         """train_utils.py:99-145: slices of the window, gripper remap, sliding-window action labels."""
@@ -358,9 +389,36 @@ class TrainStep:
         self.last_terms = {k: v.detach() for k, v in terms.items()}
         return total.detach()
 
+    def _reduce_segment(self, k):
+        """Backward-pass hook: flat-gradient segment k is complete on the compute stream -> SUM all-reduce it on the
+        communication stream (NCCL over NVLink) while the backward pass goes on."""
+        import torch.distributed as dist
+        lo, hi = self._reduced_upto, self.flat.seg_end[k]
+        if hi <= lo:
+            return
+        ev = torch.cuda.current_stream().record_event()
+        self.comm_stream.wait_event(ev)
+        with torch.cuda.stream(self.comm_stream):
+            dist.all_reduce(self.flat.G[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+        self._reduced_upto = hi
+
+    def _arm_overlap(self):
+        self._reduced_upto = 0
+        if self.overlap:
+            self.model._dvla_grad_marks = {"backbone_out": lambda: self._reduce_segment(0),
+                                           "backbone_mid": (self.flat.mid_layer, lambda: self._reduce_segment(1))}
+        elif hasattr(self.model, "_dvla_grad_marks"):
+            self.model._dvla_grad_marks = None
+
     def all_reduce_grads(self):
-        """DDP gradient mean (train.py:173): one flat bf16 all-reduce over NCCL on a side stream."""
-        all_reduce_flat(self.flat.G, self.world_size, self.pg, self.comm_stream)
+        """DDP gradient mean (train.py:173) as SUM all-reduces of the flat bf16 gradient buffer over NCCL on a side stream
+        (the 1/world factor is applied inside the clip+AdamW kernel): the segments reduced by the backward hooks, then the
+        rest here."""
+        if self.world_size == 1:
+            return
+        lo = self._reduced_upto
+        all_reduce_flat(self.flat.G[lo:] if lo else self.flat.G, self.world_size, self.pg, self.comm_stream)
+        self._reduced_upto = 0
 
     def __call__(self, batch, lr=None):
         """Micro-step: returns the (device) loss.  The reference all-reduces and clips EVERY micro-step (§2.2) and steps
@@ -375,8 +433,15 @@ class TrainStep:
 
     def micro_step(self, batch):
         ops.seed_counter(self.flat.P.device).add_(1)        # fresh dropout masks every step, also under graph replay
+        # gradients are exchanged on accumulation boundaries (same mean as DDP's per-micro-step all-reduce, train.py:173)
+        boundary = (self.micro + 1) % self.cfg.gradient_accumulation_steps == 0
+        if boundary:
+            self._arm_overlap()
+        elif hasattr(self.model, "_dvla_grad_marks"):
+            self.model._dvla_grad_marks = None
         loss = self.forward_backward(batch)
-        self.all_reduce_grads()
+        if boundary:
+            self.all_reduce_grads()
         return loss
 
 
@@ -386,6 +451,9 @@ class GraphedTrainStep:
     static device buffers (that copy IS the H2D transfer when the source is pinned host memory)."""
 
     def __init__(self, step: TrainStep, example_batch, warmup=3):
+        if step.world_size > 1 and step.cfg.gradient_accumulation_steps != 1:
+            raise ValueError("GraphedTrainStep: with world_size > 1 the captured micro-step contains the gradient all-reduce; "
+                             "use gradient_accumulation_steps == 1 or the eager TrainStep")
         self.step = step
         self.static = {k: v.clone() for k, v in example_batch.items()}
         side = torch.cuda.Stream()

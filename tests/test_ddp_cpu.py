@@ -53,3 +53,32 @@ def test_rank_seeds_shard_the_data():
     b = synthetic_batch(cfg, 1, "cpu", seed=1234 + 1)
     assert not torch.equal(a["images_primary"], b["images_primary"])
     assert a["images_primary"].shape == (1, 5, 3, 224, 224) and a["text"].shape == (1, 77)
+
+
+def test_gradient_segments_follow_backward_order():
+    """The flat gradient buffer is all-reduced in three pieces while backward runs (TrainStep._reduce_segment): segment 0
+    must only hold parameters used AFTER the backbone, segment 1 only the second half of the backbone.  A parameter that
+    feeds the backbone (projectors, resampler, query tokens, position embedding) in an early segment would be reduced
+    before its gradient exists."""
+    from dreamvla_b200.utils.train_utils import EARLY_GRAD_PREFIXES, grad_segment
+    from tests import synth
+    from tests.state_template import build_template
+    cfg = dict(synth.CASES["calvin_allheads"])
+    names = list(build_template(cfg).keys())
+    n_layers = cfg["transformer_layers"]
+    seg = {n: grad_segment(n, n_layers) for n in names}
+    feeds_backbone = ("perceiver_resampler.", "text_projector", "state_projector", "arm_state_encoder", "gripper_state_encoder",
+                      "image_primary_projector", "image_wrist_projector", "cls_token_primary_projector",
+                      "cls_token_wrist_projector", "obs_tokens", "depth_tokens", "dino_feat_tokens", "sam_feat_tokens",
+                      "trajectory_tokens", "action_pred_token", "transformer_backbone_position_embedding",
+                      "embedding_layer_norm", "vision_encoder.", "clip_model.")
+    for n in names:
+        if n.startswith(feeds_backbone):
+            assert seg[n] == 2, n
+        m = __import__("re").match(r"transformer_backbone\.h\.(\d+)\.", n)
+        if m:
+            assert seg[n] == (1 if int(m.group(1)) >= n_layers // 2 else 2), n
+        if seg[n] == 0:
+            assert n.startswith(EARLY_GRAD_PREFIXES) and "tokens" not in n.split(".")[0].replace("mask_token", ""), n
+    assert any(s == 0 for s in seg.values()) and any(s == 1 for s in seg.values())
+    assert seg["transformer_backbone.ln_f.weight"] == 1

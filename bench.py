@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=2, help="per-GPU batch (finetune.sh uses 2)")
+    ap.add_argument("--batch", type=int, default=8, help="per-GPU batch: SURVEY.md C2 measures B=2 (finetune.sh value) and B=8")
     ap.add_argument("--config", default="calvin", choices=["calvin", "libero"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -391,7 +391,7 @@ def cpu_baseline(args, steps=1, warm=0, budget_s=150.0):
         losses["loss"].backward()
         torch.nn.utils.clip_grad_norm_(params, 0.1)
         opt.step()
-        return float(losses["loss"])
+        return float(losses["loss"].detach())
     times = []
     t_all = time.perf_counter()
     for i in range(warm + steps):

@@ -26,6 +26,7 @@ batch = synthetic_batch(scfg, 2, dev, seed=77 + rank, heads=heads)
 
 def run(overlap, graphed):
     os.environ["DVLA_AR_OVERLAP"] = "1" if overlap else "0"
+    torch.manual_seed(4321 + rank)          # the DiT head draws its noise / timesteps from the global generator
     m = copy.deepcopy(base)
     st = TrainStep(m, scfg, world_size=world)
     dist.broadcast(st.flat.P, src=0)
@@ -42,9 +43,19 @@ l1, (p1, _, _, _) = run(True, False)
 l2, (p2, _, _, _) = run(True, True)
 # graphed runs one extra (warm-up) step: compare eager overlap vs eager plain exactly, graphed vs eager loosely via losses
 d = float((p0 - p1).abs().max())
-same_across_ranks = [torch.zeros_like(p1) for _ in range(world)]
-dist.all_gather(same_across_ranks, p1)
-consistent = all(torch.equal(same_across_ranks[0], t) for t in same_across_ranks)
+
+
+def ranks_agree(p):
+    g = [torch.zeros_like(p) for _ in range(world)]
+    dist.all_gather(g, p)
+    return all(torch.equal(g[0], t) for t in g)
+
+
+consistent = ranks_agree(p1)
+if rank == 0:
+    print(f"ranks hold identical parameters without overlap: {ranks_agree(p0)}")
+else:
+    ranks_agree(p0)
 if rank == 0:
     print(f"segments: seg_end={seg_end} n_big={n_big} n={p0.numel()}")
     print(f"losses plain   {l0}\nlosses overlap {l1}\nlosses overlap+graph (after 1 warm-up step) {l2}")

@@ -30,10 +30,16 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_sh
 print(prof.key_averages(group_by_input_shape=True).table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=40,
                                                            max_shapes_column_width=70))
 
-# where do the torch copy / elementwise kernels come from?  (aten ops with CUDA time, grouped by Python stack)
+# where do the torch copy / elementwise kernels come from?  (aten ops with CUDA time, with input shapes and Python stack)
 rows = []
-for e in prof.key_averages(group_by_stack_n=8):
-    if e.key.startswith("aten::") and e.self_device_time_total > 150:
-        rows.append((e.self_device_time_total, e.count, e.key, [fr for fr in e.stack if "dreamvla_b200" in fr or "bench" in fr][:3]))
-for t, n, k, st in sorted(rows, reverse=True)[:40]:
-    print(f"{t/1e3:8.3f} ms n={n:4d} {k:28s} {' <- '.join(x.split('/')[-1] for x in st)}")
+for e in prof.events():
+    if e.name in ("aten::copy_", "aten::add", "aten::cat", "aten::add_", "aten::contiguous", "aten::clone", "aten::to") \
+            and e.device_time_total > 8:
+        rows.append((e.device_time_total, e.name, str(e.input_shapes)[:90], " <- ".join(f.split("/")[-1] for f in (e.stack or [])[:5])))
+from collections import defaultdict
+agg = defaultdict(lambda: [0.0, 0])
+for t, n, sh, st in rows:
+    agg[(n, sh, st)][0] += t
+    agg[(n, sh, st)][1] += 1
+for (n, sh, st), (t, c) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:30]:
+    print(f"{t/1e3:8.3f} ms n={c:4d} {n:16s} {sh:90s} {st}")

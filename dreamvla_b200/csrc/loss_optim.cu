@@ -161,6 +161,13 @@ int silog_finish_dispatch(const void* pred, const void* label, int64_t n, const 
 // ---------------------------------------------------------------------------------------------------------------
 // Optimiser
 // ---------------------------------------------------------------------------------------------------------------
+// Global gradient norm.  The result feeds the clip factor of every data-parallel replica, so it must be BIT-identical on
+// all ranks for identical (all-reduced) gradients: block partials go to a scratch array and the last block to finish
+// (ticket counter) adds them in a fixed order -- no floating-point atomics, no dependence on block scheduling.
+constexpr int SUMSQ_MAX_BLOCKS = 2048;
+__device__ float g_sumsq_partials[SUMSQ_MAX_BLOCKS];
+__device__ unsigned int g_sumsq_ticket = 0;
+
 __global__ void __launch_bounds__(256) sumsq_kernel(const bf16* __restrict__ g, long long n, float* __restrict__ out) {
   float acc = 0.f;
   const long long nv = n >> 3;
@@ -177,13 +184,31 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const bf16* __restrict__ g, 
   if (blockIdx.x == 0)
     for (long long i = (nv << 3) + threadIdx.x; i < n; i += blockDim.x) { const float f = __bfloat162float(g[i]); acc += f * f; }
   const float t = block_sum_256(acc);
-  if (threadIdx.x == 0) atomicAdd(out, t);
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) {
+    g_sumsq_partials[blockIdx.x] = t;
+    __threadfence();
+    s_last = atomicAdd(&g_sumsq_ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    float a = 0.f;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += 256) a += __ldcg(&g_sumsq_partials[i]);
+    const float total = block_sum_256(a);
+    if (threadIdx.x == 0) {
+      out[0] += total;
+      g_sumsq_ticket = 0;
+    }
+  }
 }
 int sumsq_dispatch(const void* g, int64_t n, float* out, cudaStream_t s) {
   if (!g || !out) { set_error("sumsq: null pointer"); return DVLA_ERR_INVALID; }
   if (reinterpret_cast<uintptr_t>(g) & 15) { set_error("sumsq: buffer must be 16-byte aligned"); return DVLA_ERR_INVALID; }
   if (n <= 0) return DVLA_OK;
-  sumsq_kernel<<<grid_for(n, 256 * 8 * 4), 256, 0, s>>>((const bf16*)g, n, out);
+  unsigned blocks = grid_for(n, 256 * 8 * 4);
+  if (blocks > SUMSQ_MAX_BLOCKS) blocks = SUMSQ_MAX_BLOCKS;
+  sumsq_kernel<<<blocks, 256, 0, s>>>((const bf16*)g, n, out);
   DVLA_CHECK_LAUNCH("sumsq");
   return DVLA_OK;
 }

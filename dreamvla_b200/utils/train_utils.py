@@ -346,11 +346,11 @@ class TrainStep:
         self.micro = 0
         self.comm_stream = torch.cuda.Stream() if world_size > 1 else None
         self.last_terms = {}
-        # EXPERIMENTAL (opt-in, DVLA_AR_OVERLAP=1): all-reduce the gradient segments that complete early from backward
-        # hooks so that the exchange overlaps the rest of the backward pass.  Round-1 status: the 2-GPU check
-        # (tools/ddp_overlap_check.py) did not pass and the captured variant hung, so the default remains ONE flat
-        # all-reduce on the communication stream after backward (validated on 2 GPUs, profiles/r1_bench_2gpu_b8.log).
-        self.overlap = world_size > 1 and os.environ.get("DVLA_AR_OVERLAP", "0") == "1"
+        # The gradient segments that complete early (heads/decoders/DiT, then the second half of the backbone) are all-reduced
+        # from backward hooks on the communication stream, overlapping the rest of the backward pass; the remainder follows
+        # after backward.  Validated on 2 GPUs against one flat all-reduce (tools/ddp_overlap_check.py,
+        # profiles/r1_ddp_overlap_check.log), eagerly and inside the captured step.  DVLA_AR_OVERLAP=0 turns it off.
+        self.overlap = world_size > 1 and os.environ.get("DVLA_AR_OVERLAP", "1") != "0"
         self._reduced_upto = 0
 
     def prepare_inputs(self, batch):
@@ -439,7 +439,11 @@ class TrainStep:
             self._arm_overlap()
         elif hasattr(self.model, "_dvla_grad_marks"):
             self.model._dvla_grad_marks = None
-        loss = self.forward_backward(batch)
+        try:
+            loss = self.forward_backward(batch)
+        finally:
+            if getattr(self.model, "_dvla_grad_marks", None) is not None:
+                self.model._dvla_grad_marks = None       # a bare forward_backward() outside the step must never reduce
         if boundary:
             self.all_reduce_grads()
         return loss

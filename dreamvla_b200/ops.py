@@ -9,6 +9,8 @@ into it in its epilogue and autograd receives None; 1-D parameters (biases, Laye
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -157,6 +159,11 @@ def linear(x, weight, bias=None, *, act=None, residual=None, weight_kn=False, dr
                          float(dropout_p), float(alpha))
 
 
+# A/B switch: apply act'(pre) in the epilogue of the second layer's dgrad GEMM (DVLA_FUSE_ACT_BWD=1) instead of the separate
+# HBM-bound act_bwd kernel; see profiles/r1_notes.md for the measurements behind the default.
+_FUSE_ACT_BWD = os.environ.get("DVLA_FUSE_ACT_BWD", "0") == "1"
+
+
 class _MLP(torch.autograd.Function):
     """y = dropout(act(x W1^T + b1) W2^T + b2) + residual with the activation backward fused into the dgrad GEMM of the
     second layer (epilogue multiplies by act'(pre-activation)): no stand-alone elementwise pass in the backward."""
@@ -190,7 +197,10 @@ class _MLP(torch.autograd.Function):
         # (dZ2 W2) * act'(pre).  The GEMM can apply act' in its epilogue (aux_in), but with 8 epilogue warps per CTA that
         # made these K=1024 dgrad GEMMs epilogue-bound (+18 % GEMM time, profiles/r1_notes.md); the HBM-bound elementwise
         # kernel is cheaper until the epilogue is widened.
-        dh = L.act_bwd(L.gemm(dz2, w2, b_mn=not weight_kn), aux, act)
+        if _FUSE_ACT_BWD:
+            dh = L.gemm(dz2, w2, b_mn=not weight_kn, aux_in=aux, act=act)
+        else:
+            dh = L.act_bwd(L.gemm(dz2, w2, b_mn=not weight_kn), aux, act)
         dw1 = dw2 = db1 = db2 = dx = None
         if w2.requires_grad:
             dw2 = _accum_grad_2d(w2, h, dz2, True, True) if weight_kn else _accum_grad_2d(w2, dz2, h, True, True)

@@ -82,3 +82,23 @@ def test_gradient_segments_follow_backward_order():
             assert n.startswith(EARLY_GRAD_PREFIXES) and "tokens" not in n.split(".")[0].replace("mask_token", ""), n
     assert any(s == 0 for s in seg.values()) and any(s == 1 for s in seg.values())
     assert seg["transformer_backbone.ln_f.weight"] == 1
+
+
+def test_on_grad_ready_fires_in_backward_completion_order():
+    """ops.on_grad_ready marks: the callback of a tensor fires once everything downstream of it has run its backward --
+    heads first, then the middle of the trunk -- which is the order the gradient segments are all-reduced in."""
+    from dreamvla_b200.ops import on_grad_ready
+    events = []
+    w = [torch.randn(4, 4, requires_grad=True) for _ in range(5)]
+    x = torch.randn(3, 4)
+    h0 = x @ w[0]
+    mid = torch.tanh(h0 @ w[1])
+    on_grad_ready(mid, lambda: events.append(("mid", [wi.grad is not None for wi in w])))
+    out = torch.tanh(mid @ w[2])
+    on_grad_ready(out, lambda: events.append(("out", [wi.grad is not None for wi in w])))
+    loss = (out @ w[3]).sum() + (out @ w[4]).pow(2).sum()       # two "heads" on the trunk output
+    loss.backward()
+    assert [e[0] for e in events] == ["out", "mid"]
+    assert events[0][1] == [False, False, False, True, True]      # both heads done, trunk untouched
+    assert events[1][1] == [False, False, True, True, True]       # second half of the trunk done
+    assert all(wi.grad is not None for wi in w)

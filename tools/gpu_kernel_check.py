@@ -430,6 +430,21 @@ def group_loss():
                 max_norm=0.1, zero_grad=True)
         assert Gw.abs().max().item() == 0
     report("adamw 3 steps (bf16 param rounding)", rel(Pc, pref.detach()), 8e-3)
+    _check_sumsq_deterministic()
+
+
+def _check_sumsq_deterministic():
+    """the gradient norm feeds every replica's clip factor: same buffer -> same bits, whatever the block scheduling"""
+    g = torch.Generator(device="cpu").manual_seed(12)
+    x = torch.randn(5_000_003, generator=g).to(dev, torch.bfloat16)[:5_000_000 - 8]
+    outs = []
+    for _ in range(5):
+        o = torch.zeros(1, device=dev, dtype=torch.float32)
+        L.sumsq(x, o)
+        outs.append(o.clone())
+    ref = (x.double() ** 2).sum()
+    report("sumsq vs fp64", abs(float(outs[0]) - float(ref)) / float(ref), 1e-5)
+    report("sumsq bit-reproducible", 0.0 if all(torch.equal(outs[0], o) for o in outs) else 1.0, 0.5)
 
 
 GROUPS = {"gemm_basic": group_gemm_basic, "gemm_splitk": group_gemm_splitk, "gemm_big": group_gemm_big, "gemm_epilogue": group_gemm_epilogue,

@@ -1,9 +1,10 @@
 #!/bin/bash
 # Runs every kernel-check group in its own process (with a timeout) and collects logs under gpurun_out/.
+# CHECK_GROUPS="gemm_basic attn ..." selects groups; the attention group is repeated for every kernel variant.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv | tee gpurun_out/gpu_info.txt
-for g in ${CHECK_GROUPS:-gemm_basic gemm_epilogue gemm_big norm attn loss}; do
+for g in ${CHECK_GROUPS:-gemm_basic gemm_epilogue gemm_splitk gemm_big norm attn attn_perf loss}; do
   echo "=== $g"
   timeout ${GROUP_TIMEOUT:-240} python tools/gpu_kernel_check.py $g --json gpurun_out/check_$g.json > gpurun_out/check_$g.log 2>&1
   echo "exit=$?" >> gpurun_out/check_$g.log

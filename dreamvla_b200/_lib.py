@@ -34,7 +34,7 @@ class LayerNormFwdArgs(C.Structure):
 
 class LayerNormBwdArgs(C.Structure):
     _fields_ = [("dy", _vp), ("x", _vp), ("gamma", _vp), ("mean", _vp), ("rstd", _vp), ("dx", _vp), ("dgamma", _vp),
-                ("dbeta", _vp), ("rows", _i64), ("D", _i64), ("ld", _i64)]
+                ("dbeta", _vp), ("rows", _i64), ("D", _i64), ("ld", _i64), ("dres", _vp)]
 
 
 class AttnFwdArgs(C.Structure):
@@ -169,12 +169,14 @@ def layernorm_fwd(x2d, gamma, beta, eps, save_stats=True):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy2d, x2d, gamma, mean, rstd, dgamma_f32, dbeta_f32):
+def layernorm_bwd(dy2d, x2d, gamma, mean, rstd, dgamma_f32, dbeta_f32, dres2d=None):
+    """dx = LN'(dy) [+ dres2d]; dres2d = gradient arriving at x through a residual branch (same shape as x2d)."""
     rows, D = x2d.shape
     assert dy2d.is_contiguous() and x2d.is_contiguous()
+    assert dres2d is None or (dres2d.is_contiguous() and dres2d.shape == x2d.shape and dres2d.dtype == torch.bfloat16)
     dx = torch.empty_like(x2d)
     a = LayerNormBwdArgs(dy2d.data_ptr(), x2d.data_ptr(), _ptr(gamma), mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
-                         _ptr(dgamma_f32), _ptr(dbeta_f32), rows, D, D)
+                         _ptr(dgamma_f32), _ptr(dbeta_f32), rows, D, D, _ptr(dres2d))
     _check(load().dvla_layernorm_bwd(C.byref(a), _stream()), "dvla_layernorm_bwd")
     return dx
 

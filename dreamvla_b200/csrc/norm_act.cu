@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const bf16* __res
                                                             const bf16* __restrict__ gamma, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, bf16* __restrict__ dx,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                            long long rows, int D, long long ld) {
+                                                            long long rows, int D, long long ld,
+                                                            const bf16* __restrict__ dres) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = D >> 3;
   float pg[NV][8], pb[NV][8];
@@ -169,6 +170,12 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const bf16* __res
           const float gd = gamma ? dv[j] * gm[j] : dv[j];
           o[j] = rs * (gd - s1 - h * s2);
         }
+        if (dres) {                                   // + gradient of the residual branch that forked at x
+          float r8[8];
+          load8(dres + row * ld + vi * 8, r8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += r8[j];
+        }
         store8(dx + row * ld + vi * 8, o);
       }
     }
@@ -227,7 +234,7 @@ int layernorm_bwd_dispatch(const dvla_layernorm_bwd_args* a, cudaStream_t stream
   const long long cap = 2LL * num_sms();        // 2 resident blocks per SM; 2*D fp32 atomics per block at the end
   if (blocks > cap) blocks = cap;
 #define LN_BWD(NV) layernorm_bwd_kernel<NV><<<(unsigned)blocks, 256, 0, stream>>>((const bf16*)a->dy, (const bf16*)a->x, \
-      (const bf16*)a->gamma, a->mean, a->rstd, (bf16*)a->dx, a->dgamma, a->dbeta, a->rows, (int)a->D, a->ld)
+      (const bf16*)a->gamma, a->mean, a->rstd, (bf16*)a->dx, a->dgamma, a->dbeta, a->rows, (int)a->D, a->ld, (const bf16*)a->dres)
   switch (nv) { case 1: LN_BWD(1); break; case 2: LN_BWD(2); break; case 3: LN_BWD(3); break; default: LN_BWD(4); break; }
 #undef LN_BWD
   DVLA_CHECK_LAUNCH("layernorm_bwd");

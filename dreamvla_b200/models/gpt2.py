@@ -90,8 +90,10 @@ class GPT2Block(nn.Module):
         self.mlp = GPT2MLP(inner, config)
 
     def forward(self, hidden_states, attn_mask):
-        hidden_states = self.attn(self.ln_1(hidden_states), attn_mask, residual=hidden_states)
-        return self.mlp(self.ln_2(hidden_states), residual=hidden_states)
+        res, normed = self.ln_1.fork(hidden_states)          # the two gradients of x are summed inside LayerNorm-backward
+        hidden_states = self.attn(normed, attn_mask, residual=res)
+        res, normed = self.ln_2.fork(hidden_states)
+        return self.mlp(normed, residual=res)
 
 
 class GPT2Model(nn.Module):

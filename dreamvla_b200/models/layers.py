@@ -50,6 +50,12 @@ class LayerNorm(nn.LayerNorm):
             _require_bf16(self.weight, "LayerNorm")
         return ops.layer_norm(x, self.weight, self.bias, self.eps)
 
+    def fork(self, x):
+        """(x, LayerNorm(x)) with both gradients of x summed inside the LayerNorm-backward kernel (pre-norm residual blocks)."""
+        if self.weight is not None:
+            _require_bf16(self.weight, "LayerNorm")
+        return ops.layer_norm_fork(x, self.weight, self.bias, self.eps)
+
 
 class Attention(nn.Module):
     """timm Attention (fused qkv Linear, SDPA, proj); head_dim must be 64."""
@@ -95,5 +101,10 @@ class Block(nn.Module):
         self.mlp = Mlp(dim, int(dim * mlp_ratio), act=act)
 
     def forward(self, x):
+        if isinstance(self.norm1, LayerNorm) and isinstance(self.norm2, LayerNorm):
+            res, n = self.norm1.fork(x)
+            x = self.attn(n, residual=res)
+            res, n = self.norm2.fork(x)
+            return self.mlp(n, residual=res)
         x = self.attn(self.norm1(x), residual=x)
         return self.mlp(self.norm2(x), residual=x)

@@ -259,6 +259,51 @@ def layer_norm(x, gamma, beta, eps=1e-5):
     return _apply(_LayerNorm, x, gamma, beta, float(eps))
 
 
+class _LayerNormFork(torch.autograd.Function):
+    """(x, LN(x)) for pre-norm residual blocks `x + f(LN(x))`: the first output carries x into the residual add, so that
+    BOTH gradients of x meet in this node and the LayerNorm-backward kernel emits their sum (dres) -- autograd would
+    otherwise add them with a separate elementwise kernel per block."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        x2 = _as2d(_bf16c(x))
+        need = _grad_on and any(ctx.needs_input_grad)
+        y, mean, rstd = L.layernorm_fwd(x2, gamma, beta, eps, save_stats=need)
+        if need:
+            ctx.save_for_backward(x2, mean, rstd)
+        ctx.gamma, ctx.beta = gamma, beta
+        ctx.xshape = x.shape
+        return x.view_as(x), y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dx_res, dy):
+        x2, mean, rstd = ctx.saved_tensors
+        gamma, beta = ctx.gamma, ctx.beta
+        if dy is None:                      # LN output unused: only the pass-through gradient
+            return dx_res, None, None, None
+        dy2 = _as2d(_bf16c(dy))
+        dres2 = _as2d(_bf16c(dx_res)) if dx_res is not None else None
+        dg = db = dg32 = db32 = None
+        fused = False
+        if gamma is not None and gamma.requires_grad:
+            dg32 = getattr(gamma, "_dvla_grad32", None)
+            db32 = getattr(beta, "_dvla_grad32", None) if beta is not None else None
+            fused = dg32 is not None
+            if not fused:
+                dg32 = torch.zeros(x2.shape[1], device=x2.device, dtype=torch.float32)
+                db32 = torch.zeros(x2.shape[1], device=x2.device, dtype=torch.float32) if beta is not None else None
+        dx = L.layernorm_bwd(dy2, x2, gamma, mean, rstd, dg32, db32, dres2)
+        if dg32 is not None and not fused:
+            dg = dg32.to(torch.bfloat16)
+            db = db32.to(torch.bfloat16) if db32 is not None else None
+        return dx.view(ctx.xshape), dg, db, None
+
+
+def layer_norm_fork(x, gamma, beta, eps=1e-5):
+    """-> (x for the residual branch, LayerNorm(x)); see _LayerNormFork."""
+    return _apply(_LayerNormFork, x, gamma, beta, float(eps))
+
+
 class AttnMask:
     """Bit-matrix visibility mask + per-tile flags, built once per mask (dreamvla_model.py:25-66 semantics:
     additive 0 -> visible, -inf -> hidden).  Shared across batch and heads."""

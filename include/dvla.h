@@ -95,6 +95,8 @@ typedef struct {
   float* dgamma;      /* fp32 [D] accumulated (atomicAdd) or NULL */
   float* dbeta;       /* fp32 [D] accumulated or NULL */
   int64_t rows, D, ld;
+  const void* dres;   /* bf16 [rows, ld] or NULL: added to dx -- the gradient that reaches x through the residual branch that
+                         forks off at the LayerNorm input (x + f(LN(x)) blocks), so no separate elementwise add is needed */
 } dvla_layernorm_bwd_args;
 int dvla_layernorm_bwd(const dvla_layernorm_bwd_args* args, void* stream);
 

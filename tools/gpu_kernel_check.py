@@ -205,6 +205,9 @@ def group_norm():
             dx = L.layernorm_bwd(dy, x, gm if affine else None, mean, rstd, dg, db)
             yr.backward(dy.float())
             report(f"layernorm bwd dx {rows}x{D} affine={int(affine)}", rel(dx, xr.grad), 8e-3)
+            dres = torch.randn(rows, D, generator=g).to(dev, torch.bfloat16)       # + residual-branch gradient (fork)
+            dx2 = L.layernorm_bwd(dy, x, gm if affine else None, mean, rstd, None, None, dres)
+            report(f"layernorm bwd dx+dres {rows}x{D} affine={int(affine)}", rel(dx2, xr.grad + dres.float()), 8e-3)
             if affine:
                 report(f"layernorm bwd dgamma {rows}x{D}", rel(dg, gr.grad), 8e-3)
                 report(f"layernorm bwd dbeta {rows}x{D}", rel(db, br.grad), 8e-3)

@@ -360,12 +360,16 @@ __device__ __forceinline__ void act_bwd_mul_n(float (&v)[N], const float (&x)[N]
   }
 }
 
-// Counter-based RNG (Philox-4x32-10).  One call yields 4 uniform 32-bit words for (seed, offset).
+// Counter-based RNG (Philox-4x32, Salmon et al. SC'11).  One call yields 4 uniform 32-bit words for (seed, offset).
+// 7 rounds: the smallest round count the authors report as passing BigCrush (curand's default of 10 adds margin only);
+// the dropout masks need independent Bernoulli draws, not cryptographic strength, and the RNG is the larger half of the
+// instructions of the attention kernels' dropout path (profiles/r1_notes.md).
+constexpr int DVLA_PHILOX_ROUNDS = 7;
 __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t offset) {
   uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
   uint32_t c0 = static_cast<uint32_t>(offset), c1 = static_cast<uint32_t>(offset >> 32), c2 = 0x243F6A88u, c3 = 0x85A308D3u;
 #pragma unroll
-  for (int i = 0; i < 10; ++i) {
+  for (int i = 0; i < DVLA_PHILOX_ROUNDS; ++i) {
     uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;

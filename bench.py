@@ -285,23 +285,41 @@ def run_ours(args):
     # ---- end-to-end: pinned host inputs -> H2D -> step -> D2H loss, every step ----
     e2e = None
     if not args.no_e2e:
+        from dreamvla_b200.utils.train_utils import prefetch_to_device
         host = synthetic_batch(scfg, B, dev, seed=1234 + rank, heads=heads, pin=True)
-        dbuf = step.static if graphed else {k: torch.empty_like(v, device=dev) for k, v in host.items()}
         loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
         h2d = sum(v.numel() * v.element_size() for v in host.values())
 
-        def e2e_step():
-            for k, v in host.items():
-                dbuf[k].copy_(v, non_blocking=True)
-            ls = step(dbuf)
-            loss_host.copy_(ls.reshape(1).float(), non_blocking=True)
-        for _ in range(3):
-            e2e_step()
+        def host_batches(n):          # the data loader of this measurement: the same pinned batch, n times
+            for _ in range(n):
+                yield host
+
+        def to_device(hb):
+            return {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+
+        def e2e_run(n):
+            # the public training-loop iterator (train_one_epoch_calvin uses the same one): batch i+1 is copied host->device
+            # on a copy stream while step i runs; every step still moves its own 193 MB in and its loss out
+            for dbatch in prefetch_to_device(host_batches(n), dev, to_device):
+                ls = step(dbatch)
+                loss_host.copy_(ls.reshape(1).float(), non_blocking=True)
+        try:
+            e2e_run(3)
+        except Exception as e:  # noqa: BLE001   (keep the measurement alive: sequential copy -> step -> read-back)
+            print(f"[bench] prefetching input pipeline failed ({e!r}); measuring e2e with in-line copies", file=sys.stderr, flush=True)
+            dbuf = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+
+            def e2e_run(n):  # noqa: F811
+                for _ in range(n):
+                    for k, v in host.items():
+                        dbuf[k].copy_(v, non_blocking=True)
+                    ls = step(dbuf)
+                    loss_host.copy_(ls.reshape(1).float(), non_blocking=True)
+            e2e_run(3)
         sync_all()
         t0 = time.perf_counter()
         e0.record()
-        for _ in range(args.steps):
-            e2e_step()
+        e2e_run(args.steps)
         e1.record()
         sync_all()
         wall = (time.perf_counter() - t0) * 1e3

@@ -102,3 +102,18 @@ def test_on_grad_ready_fires_in_backward_completion_order():
     assert events[0][1] == [False, False, False, True, True]      # both heads done, trunk untouched
     assert events[1][1] == [False, False, True, True, True]       # second half of the trunk done
     assert all(wi.grad is not None for wi in w)
+
+
+def test_prefetch_iterator_host_logic():
+    """prefetch_to_device on a CPU device degenerates to a plain map: every batch, in order, exactly once (the CUDA path adds
+    a copy stream and events around the same iteration order)."""
+    from dreamvla_b200.utils.train_utils import prefetch_to_device
+    seen = []
+
+    def loader():
+        for i in range(7):
+            seen.append(i)
+            yield {"x": torch.full((2,), float(i))}
+    out = [int(b["x"][0]) for b in prefetch_to_device(loader(), "cpu", lambda hb: {k: v * 2 for k, v in hb.items()})]
+    assert out == [0, 2, 4, 6, 8, 10, 12] and seen == list(range(7))
+    assert list(prefetch_to_device(iter(()), "cpu", lambda hb: hb)) == []

@@ -139,5 +139,7 @@ def run_case(name, cfg):
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    for name, cfg in synth.CASES.items():
-        run_case(name, cfg)
+    only = sys.argv[1:]
+    for name, cfg in {**synth.CASES, **synth.CPU_ONLY_CASES}.items():
+        if not only or name in only:
+            run_case(name, cfg)

@@ -26,6 +26,14 @@ CASES = {
                          atten_only_obs=True, attn_robot_proprio_state=True, mask_l_obs_ratio=0.0, phase="evaluate"),
 }
 
+# Cases pinned on the CPU only (reference -> golden -> oracle): constructor switches of the shipped scripts that the three
+# GPU cases above do not exercise.  Not in CASES so that the GPU suite keeps its size.
+CPU_ONLY_CASES = {
+    # LIBERO scripts pass --gripper_width: 8-dim state, the 2-dim gripper opening goes straight into gripper_state_encoder
+    "libero_gripper_width": dict(BASE, obs_pred=False, depth_pred=False, trajectory_pred=False, dino_feat_pred=False,
+                                 sam_feat_pred=False, use_dit_head=True, sequence_length=3, gripper_width=True),
+}
+
 CTOR_KEYS = ("sequence_length", "num_resampler_query", "num_obs_token_per_image", "obs_pred", "atten_only_obs",
              "attn_robot_proprio_state", "atten_goal", "atten_goal_state", "mask_l_obs_ratio", "action_pred_steps",
              "transformer_layers", "hidden_dim", "transformer_heads", "phase", "gripper_width", "pred_num", "depth_pred",
@@ -81,8 +89,11 @@ def synth_inputs(cfg):
     g = torch.Generator(device="cpu").manual_seed(cfg["input_seed"])
     image_primary = torch.randn(B, S, 3, 224, 224, generator=g)
     image_wrist = torch.randn(B, S, 3, 224, 224, generator=g)
-    state = torch.randn(B, S, 7, generator=g) * 0.5
-    state[..., 6] = (torch.rand(B, S, generator=g) < 0.5).float()
+    if cfg.get("gripper_width", False):       # 6 arm dims + 2 finger positions (dreamvla_model.py:656-664)
+        state = torch.randn(B, S, 8, generator=g) * 0.5
+    else:
+        state = torch.randn(B, S, 7, generator=g) * 0.5
+        state[..., 6] = (torch.rand(B, S, generator=g) < 0.5).float()
     text = torch.zeros(B, 77, dtype=torch.long)
     for b in range(B):
         k = int(torch.randint(3, 21, (1,), generator=g))

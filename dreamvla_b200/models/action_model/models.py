@@ -12,7 +12,6 @@ import math
 import torch
 import torch.nn as nn
 
-from ... import ops
 from ..layers import Block, LayerNorm, Linear
 
 

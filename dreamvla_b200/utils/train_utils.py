@@ -593,10 +593,19 @@ def train_one_epoch_calvin(args, model, epoch, calvin_loader, optimizer, lr_sche
     step_time_m, data_time_m = AverageMeter(), AverageMeter()
     end = time.time()
     dev = torch.device("cuda", device_id) if isinstance(device_id, int) else torch.device(device_id)
+    # --cuda_graph: after ONE eager step (allocator pools, NCCL communicator and lazy tables are warm) the micro-step and the
+    # optimiser step are captured once and replayed for every later batch of the same shapes (gradient accumulation 1 only)
+    use_graph = bool(getattr(args, "cuda_graph", False)) and args.gradient_accumulation_steps == 1
+    graphed = getattr(core, "_dvla_graphed_step", None)
     for num_steps, batch in enumerate(prefetch_to_device(calvin_loader, dev, lambda bc: batch_from_tuple(bc, dev))):
         data_time_m.update(time.time() - end)
         lr = lr_scheduler.get_last_lr()[0] if lr_scheduler is not None else args.learning_rate
-        loss = state(batch, lr=lr)
+        if use_graph and graphed is None and state.micro > 0:
+            graphed = GraphedTrainStep(state, batch, warmup=0)
+            core._dvla_graphed_step = graphed
+        replay = graphed is not None and batch.keys() == graphed.static.keys() and \
+            all(batch[k].shape == graphed.static[k].shape for k in batch)
+        loss = graphed(batch, lr=lr) if replay else state(batch, lr=lr)
         if (num_steps + 1) % args.gradient_accumulation_steps == 0:
             if lr_scheduler is not None:
                 lr_scheduler.step()

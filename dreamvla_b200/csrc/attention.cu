@@ -1,8 +1,9 @@
 // Flash-style multi-head attention for head_dim = 64 with a bit-matrix visibility mask and tile skipping.
 //
-// v1 data path: cp.async -> XOR-swizzled smem tiles -> ldmatrix -> mma.sync.m16n8k16 (bf16, fp32 accumulate),
-// online softmax in registers, no [Lq,Lk] tensor in HBM.  (Attention is 3-4 % of the path's FLOPs -- SURVEY §8d --
-// the tcgen05 budget of this round went to the GEMM; a tcgen05/TMEM variant of this kernel is the next step.)
+// Data path of THIS file: cp.async -> XOR-swizzled smem tiles -> ldmatrix -> mma.sync.m16n8k16 (bf16, fp32 accumulate),
+// online softmax in registers, no [Lq,Lk] tensor in HBM.  These kernels serve the short sequences of the path (DiT: 4
+// tokens, resampler: 16 queries) and strides a tensor map cannot express; sequences of >= 96 tokens go to the
+// warp-specialised tcgen05 / TMEM kernels of attention_fwd_ws.cu / attention_bwd_ws.cu through the dispatchers below.
 //
 // Kernels:
 //   attn_fwd_kernel     grid (ceil(Lq/64), H, B), 4 warps x 16 query rows, K/V tiles of 64 keys double-buffered

@@ -194,9 +194,9 @@ class _MLP(torch.autograd.Function):
         dy2 = _as2d(_bf16c(dy))
         d_res = dy.view(res_shape) if res_shape is not None and ctx.needs_input_grad[5] else None
         dz2 = L.dropout(dy2, dropout_p, seed, seed_ptr=seed_counter(dy2.device)) if dropout_p > 0 else dy2
-        # (dZ2 W2) * act'(pre).  The GEMM can apply act' in its epilogue (aux_in), but with 8 epilogue warps per CTA that
-        # made these K=1024 dgrad GEMMs epilogue-bound (+18 % GEMM time, profiles/r1_notes.md); the HBM-bound elementwise
-        # kernel is cheaper until the epilogue is widened.
+        # (dZ2 W2) * act'(pre).  The GEMM can apply act' in its epilogue (aux_in): measured +18 % GEMM time with 8 epilogue
+        # warps per CTA and still no gain with 16 (104.9 vs 104.3 ms/step, profiles/r1_notes.md), so the HBM-bound
+        # elementwise kernel stays the default.
         if _FUSE_ACT_BWD:
             dh = L.gemm(dz2, w2, b_mn=not weight_kn, aux_in=aux, act=act)
         else:

@@ -8,8 +8,10 @@ Here:
   * FlatParams keeps parameters, gradients and AdamW moments in flat buffers; weight gradients are accumulated straight
     into the flat gradient buffer by the wgrad GEMM epilogue (ops.py), 1-D gradients in an fp32 side buffer;
   * losses are fused value+gradient kernels (ops.mse_loss / cosine_loss / silog_loss), no host sync in the step;
-  * data-parallel: ONE bf16 all-reduce (NCCL over NVLink) of the flat gradient buffer per micro-step on a side stream,
-    then global-norm clip + AdamW fused in two kernels (dvla_sumsq, dvla_adamw); lr / step counters live on the device.
+  * data-parallel: the flat bf16 gradient buffer is laid out in order of backward completion and all-reduced (NCCL over
+    NVLink, communication stream) in three segments, the first two from backward hooks while backward continues; then
+    an order-deterministic global norm + clip + AdamW in two kernels (dvla_sumsq, dvla_adamw); lr / step counters live
+    on the device;
   * the per-step `.cpu().numpy()` visual-debug copies of the reference (:198-213, :382-396) are not part of the path.
 """
 from __future__ import annotations

@@ -78,3 +78,21 @@ def test_graph_replay_matches_eager(dev):
         tol = 2e-2 if i == 0 else 8e-2
         assert abs(a - b) < tol * abs(a) + 1e-4, (losses_e, losses_g)
     assert losses_e[-1] < losses_e[0]                     # the step actually trains on a fixed batch
+
+
+def test_prefetch_to_device_delivers_every_batch(dev):
+    """The copy-stream input iterator (train_one_epoch_calvin, bench.py e2e): batches arrive complete, in order, as device
+    tensors, while the consumer keeps the compute stream busy."""
+    from dreamvla_b200.utils.train_utils import prefetch_to_device
+    g = torch.Generator().manual_seed(3)
+    host = [{"x": torch.randn(1 << 20, generator=g).pin_memory(), "i": torch.full((4,), i).pin_memory()} for i in range(6)]
+    busy = torch.randn(2048, 2048, device=dev)
+    seen = []
+    for b in prefetch_to_device(iter(host), dev, lambda hb: {k: v.to(dev, non_blocking=True) for k, v in hb.items()}):
+        busy = busy @ busy * 1e-3                       # compute-stream work the next copy overlaps with
+        assert b["x"].is_cuda and b["i"].is_cuda
+        seen.append((int(b["i"][0]), b["x"].clone()))
+    torch.cuda.synchronize()
+    assert [i for i, _ in seen] == list(range(6))
+    for (i, x), h in zip(seen, host):
+        assert torch.equal(x.cpu(), h["x"]), i

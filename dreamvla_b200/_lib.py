@@ -68,7 +68,7 @@ EXPORTS = [
     "dvla_version", "dvla_last_error", "dvla_launch_count", "dvla_gemm", "dvla_layernorm_fwd", "dvla_layernorm_bwd",
     "dvla_attn_fwd", "dvla_attn_bwd", "dvla_attn_mask_tiles", "dvla_colsum_accum", "dvla_accum_fp32_into_bf16",
     "dvla_dropout", "dvla_act_bwd", "dvla_mse_loss", "dvla_cosine_loss", "dvla_silog_stats", "dvla_silog_finish",
-    "dvla_sumsq", "dvla_adamw",
+    "dvla_sumsq", "dvla_adamw", "dvla_grad_clip_scale",
 ]
 
 _lib = None
@@ -314,3 +314,9 @@ def adamw(p, g, m, v, *, sumsq_t, lr_t, step_t, beta1, beta2, eps, weight_decay,
     a = AdamWArgs(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), _ptr(sumsq_t), lr_t.data_ptr(),
                   step_t.data_ptr(), beta1, beta2, eps, weight_decay, max_norm, grad_scale, int(zero_grad))
     _check(load().dvla_adamw(C.byref(a), _stream()), "dvla_adamw")
+
+
+def grad_clip_scale(g, sumsq_t, max_norm, grad_scale=1.0):
+    """g *= grad_scale * min(1, max_norm / (sqrt(sumsq) * grad_scale + 1e-6)) in place (clip_grad_norm_ on the flat buffer)."""
+    _check(load().dvla_grad_clip_scale(C.c_void_p(g.data_ptr()), _i64(g.numel()), C.c_void_p(sumsq_t.data_ptr()),
+                                       _f32(max_norm), _f32(grad_scale), _stream()), "dvla_grad_clip_scale")

@@ -213,6 +213,38 @@ int sumsq_dispatch(const void* g, int64_t n, float* out, cudaStream_t s) {
   return DVLA_OK;
 }
 
+// In-place clip of the (rank-summed) accumulated gradient: g *= grad_scale * min(1, max_norm / (||g||*grad_scale + 1e-6)).
+// Reference utils/train_utils.py:599-600 clips the ACCUMULATED gradient after every micro-step; with gradient accumulation
+// that clip must land in the buffer itself (the fused clip inside adamw_kernel only covers accumulation == 1).
+__global__ void __launch_bounds__(256) grad_clip_scale_kernel(bf16* __restrict__ g, long long n, const float* __restrict__ sumsq,
+                                                              float max_norm, float grad_scale) {
+  const float norm = sqrtf(sumsq[0]) * grad_scale;
+  const float c = grad_scale * fminf(1.0f, max_norm / (norm + 1e-6f));
+  if (c == 1.0f) return;
+  const long long nv = n >> 3;
+  uint4* gv = reinterpret_cast<uint4*>(g);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nv;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    uint4 u = gv[i];
+    float2 t;
+    t = unpack_bf16x2(u.x); u.x = pack_bf16x2(t.x * c, t.y * c);
+    t = unpack_bf16x2(u.y); u.y = pack_bf16x2(t.x * c, t.y * c);
+    t = unpack_bf16x2(u.z); u.z = pack_bf16x2(t.x * c, t.y * c);
+    t = unpack_bf16x2(u.w); u.w = pack_bf16x2(t.x * c, t.y * c);
+    gv[i] = u;
+  }
+  if (blockIdx.x == 0)
+    for (long long i = (nv << 3) + threadIdx.x; i < n; i += blockDim.x) g[i] = __float2bfloat16(__bfloat162float(g[i]) * c);
+}
+int grad_clip_scale_dispatch(void* g, int64_t n, const float* sumsq, float max_norm, float grad_scale, cudaStream_t s) {
+  if (!g || !sumsq) { set_error("grad_clip_scale: null pointer"); return DVLA_ERR_INVALID; }
+  if (reinterpret_cast<uintptr_t>(g) & 15) { set_error("grad_clip_scale: buffer must be 16-byte aligned"); return DVLA_ERR_INVALID; }
+  if (n <= 0) return DVLA_OK;
+  grad_clip_scale_kernel<<<grid_for(n, 256 * 8 * 4), 256, 0, s>>>((bf16*)g, n, sumsq, max_norm, grad_scale);
+  DVLA_CHECK_LAUNCH("grad_clip_scale");
+  return DVLA_OK;
+}
+
 struct AdamWParams {
   bf16* p; bf16* g; float* m; float* v; long long n;
   const float* sumsq; const float* lr; const float* step;

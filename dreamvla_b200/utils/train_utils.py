@@ -154,10 +154,16 @@ class StepConfig:
     weight_decay: float = 1e-4
     max_grad_norm: float = 0.1
     gripper_width: bool = False
+    # True (reference semantics, utils/train_utils.py:599-600 + DDP without no_sync): the gradient is all-reduced and the
+    # ACCUMULATED gradient is clipped in place after EVERY micro-step.  False: one exchange + one clip per optimiser step
+    # (cheaper, but a different update whenever gradient_accumulation_steps > 1).
+    reduce_every_micro_step: bool = True
 
     @staticmethod
     def from_args(args):
         kw = {f: getattr(args, f) for f in StepConfig.__dataclass_fields__ if hasattr(args, f)}
+        if getattr(args, "exchange_on_boundary_only", False):
+            kw["reduce_every_micro_step"] = False
         return StepConfig(**kw)
 
 
@@ -227,17 +233,45 @@ class FlatParams:
             L.accum_fp32_into_bf16(self.G32[: self.n - self.n_big], self.G[self.n_big:])
             self.G32.zero_()
 
-    def optimizer_step(self, cfg: StepConfig, lr: float | None, world_size: int = 1):
-        """clip_grad_norm_(max_norm) on the rank-averaged gradient + AdamW (train_utils.py:600-608); zeroes G.
-        lr=None keeps the device-resident lr (set outside a captured CUDA graph)."""
+    def clip_in_place(self, cfg: StepConfig, world_size: int = 1):
+        """G <- clip_grad_norm_(G / world, max_norm) in the buffer itself: what the reference does to the accumulated .grad
+        after every micro-step (train_utils.py:599-600); G holds the rank SUM when this is called."""
         self.sumsq.zero_()
         L.sumsq(self.G, self.sumsq)
+        L.grad_clip_scale(self.G, self.sumsq, cfg.max_grad_norm, 1.0 / world_size)
+
+    def optimizer_step(self, cfg: StepConfig, lr: float | None, world_size: int = 1, preclipped: bool = False):
+        """clip_grad_norm_(max_norm) on the rank-averaged gradient + AdamW (train_utils.py:600-608); zeroes G.
+        lr=None keeps the device-resident lr (set outside a captured CUDA graph).  preclipped=True: G already holds the
+        rank mean, clipped by `clip_in_place` (gradient accumulation with the reference's per-micro-step clip)."""
         if lr is not None:
             self.lr.fill_(lr)
         self.step_count += 1
+        if preclipped:
+            L.adamw(self.P, self.G, self.m, self.v, sumsq_t=None, lr_t=self.lr, step_t=self.step_count, beta1=0.9,
+                    beta2=0.999, eps=1e-8, weight_decay=cfg.weight_decay, max_norm=cfg.max_grad_norm, grad_scale=1.0,
+                    zero_grad=True)
+            return
+        self.sumsq.zero_()
+        L.sumsq(self.G, self.sumsq)
         L.adamw(self.P, self.G, self.m, self.v, sumsq_t=self.sumsq, lr_t=self.lr, step_t=self.step_count, beta1=0.9,
                 beta2=0.999, eps=1e-8, weight_decay=cfg.weight_decay, max_norm=cfg.max_grad_norm,
                 grad_scale=1.0 / world_size, zero_grad=True)
+
+    def optimizer_state_dict(self):
+        """AdamW state of the flat buffers.  NOT torch.optim.AdamW's format (the reference's `optimizer_state_dict`,
+        train.py:283, is index-keyed over its own parameter list and holds bf16 moments): moments here are fp32 and keyed by
+        the parameter names in `names`, in flat-buffer order."""
+        return {"format": "dvla_flat_adamw_v1", "names": list(self.names), "numel": [p.numel() for _, p in self.params],
+                "m": self.m.detach().cpu(), "v": self.v.detach().cpu(), "step": self.step_count.detach().cpu()}
+
+    def load_optimizer_state_dict(self, sd):
+        if sd.get("names") != list(self.names) or tuple(sd["m"].shape) != tuple(self.m.shape):
+            raise RuntimeError("optimizer state does not match this model's trainable parameter set "
+                               "(saved by a different head configuration?)")
+        self.m.copy_(sd["m"])
+        self.v.copy_(sd["v"])
+        self.step_count.copy_(sd["step"].reshape(-1)[:1])
 
 
 def build_labels(cfg: StepConfig, batch, need):
@@ -341,11 +375,26 @@ class TrainStep:
     """One micro-step of train_utils.py:94-608 on device-resident inputs; see module docstring."""
 
     def __init__(self, model, cfg: StepConfig, world_size=1, process_group=None):
+        if cfg.pred_num != 1:
+            # the reference unfolds the labels over pred_num (train_utils.py:176-185); this step builds single-frame labels
+            raise NotImplementedError("pred_num > 1 is not implemented in the train step (labels are not unfolded)")
         self.model, self.cfg = model, cfg
         self.world_size = world_size
         self.pg = process_group
         self.flat = FlatParams(model, cfg)
-        self.micro = 0
+        if world_size > 1:
+            # DDP's constructor broadcasts rank 0's parameters and buffers (train.py:173); every replica must start from
+            # the same weights or the shared all-reduced gradient is applied to different models
+            import torch.distributed as dist
+            dist.broadcast(self.flat.P, src=0, group=process_group)
+            for _, b in model.named_buffers():
+                if b.is_cuda:
+                    dist.broadcast(b, src=0, group=process_group)
+            for name, p in model.named_parameters():
+                if p.is_cuda and not name.startswith("clip_model.") and getattr(p, "_dvla_grad", None) is None:
+                    dist.broadcast(p.data, src=0, group=process_group)
+        self.micro = 0            # position inside the current accumulation window
+        self.total_micro = 0      # micro-steps since construction
         self.comm_stream = torch.cuda.Stream() if world_size > 1 else None
         self.last_terms = {}
         # The gradient segments that complete early (heads/decoders/DiT, then the second half of the backbone) are all-reduced
@@ -373,7 +422,9 @@ class TrainStep:
         return dict(image_primary=batch["images_primary"][:, :S], image_wrist=batch["images_wrist"][:, :S],
                     state=input_states[:, :S], text_token=text, action_label=label_actions[:, :S - cfg.atten_goal])
 
-    def forward_backward(self, batch):
+    def forward_backward(self, batch, draws=None):
+        """`draws` (tests): {"diffusion_noise", "diffusion_timestep", "diffusion_drop_ids"} -- the tensors the DiT loss samples
+        (action_model.py:59-60, models.py:83), injected so a run can be lined up with the reference's recorded draws."""
         cfg = self.cfg
         inp = self.prepare_inputs(batch)
         need = dict(image=cfg.loss_image, depth=cfg.loss_depth, dino=cfg.loss_dino_feat, sam=cfg.loss_sam_feat,
@@ -381,7 +432,7 @@ class TrainStep:
         labels = build_labels(cfg, batch, need)
         labels["actions"] = inp["action_label"]
         outputs = self.model(inp["image_primary"], inp["image_wrist"], inp["state"], inp["text_token"], action=None,
-                             action_label=inp["action_label"])
+                             action_label=inp["action_label"], **(draws or {}))
         terms = compute_losses(cfg, outputs, labels, bs=inp["state"].shape[0])
         total = None
         for t in terms.values():
@@ -422,32 +473,47 @@ class TrainStep:
         all_reduce_flat(self.flat.G[lo:] if lo else self.flat.G, self.world_size, self.pg, self.comm_stream)
         self._reduced_upto = 0
 
-    def __call__(self, batch, lr=None):
-        """Micro-step: returns the (device) loss.  The reference all-reduces and clips EVERY micro-step (§2.2) and steps
-        the optimiser on accumulation boundaries (train_utils.py:599-608)."""
+    @property
+    def per_micro_clip(self):
+        """Reference accumulation semantics: reduce + clip the accumulated gradient in place after every micro-step."""
+        return self.cfg.reduce_every_micro_step and self.cfg.gradient_accumulation_steps > 1
+
+    def is_boundary(self, boundary=None):
+        return ((self.micro + 1) % self.cfg.gradient_accumulation_steps == 0) if boundary is None else bool(boundary)
+
+    def __call__(self, batch, lr=None, boundary=None, draws=None):
+        """Micro-step: returns the (device) loss.  The reference all-reduces (DDP, no no_sync) and clips the accumulated
+        gradient EVERY micro-step and steps the optimiser on accumulation boundaries and on the last batch of an epoch
+        (train_utils.py:599-608); `boundary` overrides the internal counter for that last-batch case."""
         cfg = self.cfg
         self.flat.lr.fill_(cfg.learning_rate if lr is None else lr)
-        loss = self.micro_step(batch)
+        b = self.is_boundary(boundary)
+        loss = self.micro_step(batch, boundary=b, draws=draws)
         self.micro += 1
-        if self.micro % cfg.gradient_accumulation_steps == 0:
-            self.flat.optimizer_step(cfg, None, self.world_size)
+        self.total_micro += 1
+        if b:
+            self.flat.optimizer_step(cfg, None, self.world_size, preclipped=self.per_micro_clip)
+            self.micro = 0
         return loss
 
-    def micro_step(self, batch):
+    def micro_step(self, batch, boundary=None, draws=None):
         ops.seed_counter(self.flat.P.device).add_(1)        # fresh dropout masks every step, also under graph replay
-        # gradients are exchanged on accumulation boundaries (same mean as DDP's per-micro-step all-reduce, train.py:173)
-        boundary = (self.micro + 1) % self.cfg.gradient_accumulation_steps == 0
-        if boundary:
+        boundary = self.is_boundary(boundary)
+        # reference semantics: exchange every micro-step; otherwise only on accumulation boundaries (same mean, one clip)
+        exchange = boundary or self.cfg.reduce_every_micro_step
+        if exchange:
             self._arm_overlap()
         elif hasattr(self.model, "_dvla_grad_marks"):
             self.model._dvla_grad_marks = None
         try:
-            loss = self.forward_backward(batch)
+            loss = self.forward_backward(batch, draws)
         finally:
             if getattr(self.model, "_dvla_grad_marks", None) is not None:
                 self.model._dvla_grad_marks = None       # a bare forward_backward() outside the step must never reduce
-        if boundary:
+        if exchange:
             self.all_reduce_grads()
+        if self.per_micro_clip:
+            self.flat.clip_in_place(self.cfg, self.world_size)
         return loss
 
 
@@ -457,9 +523,10 @@ class GraphedTrainStep:
     static device buffers (that copy IS the H2D transfer when the source is pinned host memory)."""
 
     def __init__(self, step: TrainStep, example_batch, warmup=3):
-        if step.world_size > 1 and step.cfg.gradient_accumulation_steps != 1:
-            raise ValueError("GraphedTrainStep: with world_size > 1 the captured micro-step contains the gradient all-reduce; "
-                             "use gradient_accumulation_steps == 1 or the eager TrainStep")
+        if step.world_size > 1 and step.cfg.gradient_accumulation_steps != 1 and not step.cfg.reduce_every_micro_step:
+            raise ValueError("GraphedTrainStep: the captured micro-step contains the gradient all-reduce; with "
+                             "reduce_every_micro_step=False and world_size > 1 use gradient_accumulation_steps == 1 or the "
+                             "eager TrainStep")
         self.step = step
         self.static = {k: v.clone() for k, v in example_batch.items()}
         side = torch.cuda.Stream()
@@ -472,23 +539,28 @@ class GraphedTrainStep:
         n0 = L.launch_count()
         self.g_micro = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_micro):
-            self.loss = step.micro_step(self.static)
+            # with the reference's accumulation semantics every micro-step is the same graph (exchange + in-place clip);
+            # without accumulation it is the boundary step
+            self.loss = step.micro_step(self.static, boundary=step.cfg.gradient_accumulation_steps == 1 or None)
         self.g_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_opt, pool=self.g_micro.pool()):
-            step.flat.optimizer_step(step.cfg, None, step.world_size)
+            step.flat.optimizer_step(step.cfg, None, step.world_size, preclipped=step.per_micro_clip)
         self.launches_per_step = L.launch_count() - n0      # libdvla kernels recorded in the two graphs
 
-    def __call__(self, batch, lr=None):
+    def __call__(self, batch, lr=None, boundary=None):
         st = self.step
         if batch is not self.static:
             for k, v in batch.items():
                 self.static[k].copy_(v, non_blocking=True)
         if lr is not None:
             st.flat.lr.fill_(lr)
+        b = st.is_boundary(boundary)
         self.g_micro.replay()
         st.micro += 1
-        if st.micro % st.cfg.gradient_accumulation_steps == 0:
+        st.total_micro += 1
+        if b:
             self.g_opt.replay()
+            st.micro = 0
         return self.loss
 
 
@@ -597,18 +669,24 @@ def train_one_epoch_calvin(args, model, epoch, calvin_loader, optimizer, lr_sche
     dev = torch.device("cuda", device_id) if isinstance(device_id, int) else torch.device(device_id)
     # --cuda_graph: after ONE eager step (allocator pools, NCCL communicator and lazy tables are warm) the micro-step and the
     # optimiser step are captured once and replayed for every later batch of the same shapes (gradient accumulation 1 only)
-    use_graph = bool(getattr(args, "cuda_graph", False)) and args.gradient_accumulation_steps == 1
+    use_graph = bool(getattr(args, "cuda_graph", False)) and (args.gradient_accumulation_steps == 1
+                                                               or state.cfg.reduce_every_micro_step)
+    n_batches = getattr(calvin_loader, "num_batches", None)
+    accum = args.gradient_accumulation_steps
+    state.micro = 0           # the reference counts accumulation windows from the start of each epoch (:602)
     graphed = getattr(core, "_dvla_graphed_step", None)
     for num_steps, batch in enumerate(prefetch_to_device(calvin_loader, dev, lambda bc: batch_from_tuple(bc, dev))):
         data_time_m.update(time.time() - end)
         lr = lr_scheduler.get_last_lr()[0] if lr_scheduler is not None else args.learning_rate
-        if use_graph and graphed is None and state.micro > 0:
+        if use_graph and graphed is None and state.total_micro > 0:
             graphed = GraphedTrainStep(state, batch, warmup=0)
             core._dvla_graphed_step = graphed
         replay = graphed is not None and batch.keys() == graphed.static.keys() and \
             all(batch[k].shape == graphed.static[k].shape for k in batch)
-        loss = graphed(batch, lr=lr) if replay else state(batch, lr=lr)
-        if (num_steps + 1) % args.gradient_accumulation_steps == 0:
+        # optimiser step on accumulation boundaries AND on the last batch of the epoch (train_utils.py:602-604)
+        boundary = (num_steps + 1) % accum == 0 or (n_batches is not None and num_steps == n_batches - 1)
+        loss = graphed(batch, lr=lr, boundary=boundary) if replay else state(batch, lr=lr, boundary=boundary)
+        if boundary:
             if lr_scheduler is not None:
                 lr_scheduler.step()
             step_time_m.update(time.time() - end)

@@ -201,6 +201,9 @@ typedef struct {
   int32_t zero_grad;
 } dvla_adamw_args;
 int dvla_adamw(const dvla_adamw_args* args, void* stream);
+/* In-place clip of the accumulated gradient, every micro-step, as utils/train_utils.py:599-600 does
+ * (clip_grad_norm_ on .grad that keeps accumulating):  g *= grad_scale * min(1, max_norm / (sqrt(sumsq)*grad_scale + 1e-6)). */
+int dvla_grad_clip_scale(void* g_bf16, int64_t n, const float* sumsq, float max_norm, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

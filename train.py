@@ -7,8 +7,10 @@ Builds `DreamVLA` from the reference's flags, casts to bf16 (`--precision bf16`;
 one process per GPU over NCCL, and runs `train_one_epoch_calvin` (dreamvla_b200/utils/train_utils.py).  Dataset loading
 (utils/data_utils.py in the reference) is out of scope: pass `--synthetic_steps N` to train on the synthetic collator
 contract, or plug a loader that yields the reference's 13-tuple (data_utils.py:1395-1397) into `main(args, loader)`.
-Checkpoints keep the reference's ABI (train.py:279-289): {"epoch", "model_state_dict" ("module."-prefixed, trainable
-parameters only), "optimizer_state_dict", "lr_scheduler_state_dict"}.
+Checkpoints keep the reference's layout (train.py:279-289): {"epoch", "model_state_dict" ("module."-prefixed, trainable
+parameters only; loadable by the reference and vice versa), "optimizer_state_dict", "lr_scheduler_state_dict"}.  The two
+optimiser/scheduler entries are this package's own formats (flat fp32 AdamW moments keyed by parameter name; a step index)
+and are restored on --resume_from_checkpoint; they are not interchangeable with torch.optim.AdamW / HF scheduler states.
 """
 from __future__ import annotations
 
@@ -19,16 +21,45 @@ import random
 import numpy as np
 import torch
 
+from dreamvla_b200 import ops
 from dreamvla_b200.models import DreamVLA
 from dreamvla_b200.utils.arguments_utils import get_parser, model_kwargs
 from dreamvla_b200.utils.distributed_utils import init_distributed_device, world_info_from_env
-from dreamvla_b200.utils.train_utils import StepConfig, synthetic_batch, train_one_epoch_calvin
+from dreamvla_b200.utils.train_utils import StepConfig, TrainStep, synthetic_batch, train_one_epoch_calvin
 
 
 def random_seed(seed=42, rank=0):           # train.py:23-26
     torch.manual_seed(seed + rank)
     np.random.seed(seed + rank)
     random.seed(seed + rank)
+    ops.manual_seed(seed + rank)            # the kernels' Philox dropout stream follows --seed (and differs per rank)
+
+
+class CosineRestartSchedule:
+    """torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(T_0=10, T_mult=2, eta_min=1e-7) stepped once per optimiser step
+    with no epoch argument (train.py:205-206, train_utils.py:605): closed form of its T_cur / T_i recurrence."""
+
+    def __init__(self, base_lr, T_0=10, T_mult=2, eta_min=1e-7):
+        self.base_lr, self.T_0, self.T_mult, self.eta_min, self.step_idx = base_lr, T_0, T_mult, eta_min, 0
+
+    def lr_at(self, s):
+        T_i, t = self.T_0, s
+        while t >= T_i:
+            t -= T_i
+            T_i *= self.T_mult
+        return self.eta_min + (self.base_lr - self.eta_min) * (1 + math.cos(math.pi * t / T_i)) / 2
+
+    def get_last_lr(self):
+        return [self.lr_at(self.step_idx)]
+
+    def step(self):
+        self.step_idx += 1
+
+    def state_dict(self):
+        return {"step_idx": self.step_idx}
+
+    def load_state_dict(self, sd):
+        self.step_idx = sd["step_idx"]
 
 
 class WarmupSchedule:
@@ -109,7 +140,7 @@ def get_checkpoint(model):                  # train_utils.py:750-757
 def main(args, loader=None):
     args.local_rank, args.rank, args.world_size = world_info_from_env()
     device_id = init_distributed_device(args)
-    random_seed(args.seed, args.rank)
+    random_seed(args.seed)                   # train.py:50: every rank builds the SAME initial model
     if args.precision not in ("bf16", "amp_bf16", "amp_bfloat16"):
         raise SystemExit("dreamvla_b200 kernels are bf16-only: run with --precision bf16")
     model = DreamVLA(finetune_type=args.finetune_type, clip_device="cpu", vit_checkpoint_path=args.vit_checkpoint_path,
@@ -120,14 +151,20 @@ def main(args, loader=None):
     model = model.to(device_id)
     model._init_model_type()
     ddp_model = _ModuleWrapper(model)
+    random_seed(args.seed, args.rank)        # train.py:110: data order / dropout / diffusion draws differ per rank
     if loader is None:
         if args.synthetic_steps <= 0:
             raise SystemExit("dataset loading is out of scope of this package: pass --synthetic_steps N or call "
                              "main(args, loader) with a loader yielding the reference's 13-tuple batches")
         loader = SyntheticLoader(args, device_id, args.synthetic_steps)
     total_steps = loader.num_batches * args.num_epochs
-    sched = WarmupSchedule(args.learning_rate, args.lr_scheduler, loader.num_batches * args.warmup_epochs // max(args.gradient_accumulation_steps, 1),
-                           total_steps // max(args.gradient_accumulation_steps, 1))
+    accum = max(args.gradient_accumulation_steps, 1)
+    if args.lr_scheduler == "cosine_restart":
+        sched = CosineRestartSchedule(args.learning_rate)
+    else:                                    # train.py:179-210 (the "+ 1" only when accumulating)
+        extra = 1 if accum > 1 else 0
+        sched = WarmupSchedule(args.learning_rate, args.lr_scheduler, loader.num_batches * args.warmup_epochs // accum + extra,
+                               total_steps // accum + extra)
     resume_from_epoch = 0
     if args.finetune_from_pretrained_ckpt is not None:   # train.py:212-250 key surgery
         ckpt = torch.load(args.finetune_from_pretrained_ckpt, map_location="cpu")["model_state_dict"]
@@ -143,12 +180,23 @@ def main(args, loader=None):
         if pe in ckpt and ckpt[pe].shape != model.transformer_backbone_position_embedding.shape:
             ckpt[pe] = ckpt[pe][:, :args.sequence_length, :, :]
         ddp_model.load_state_dict(ckpt, False)
-    state = None
+    opt_state = None
     if args.resume_from_checkpoint is not None:
         ck = torch.load(args.resume_from_checkpoint, map_location="cpu")
         ddp_model.load_state_dict(ck["model_state_dict"], False)
+        opt_state = ck.get("optimizer_state_dict")
         sched.load_state_dict(ck["lr_scheduler_state_dict"])
         resume_from_epoch = ck["epoch"] + 1
+    # The flat parameter / gradient / AdamW-moment buffers (the optimiser of this package) are built AFTER every checkpoint
+    # load: parameters become views of one buffer, rank 0's copy is broadcast (DDP constructor semantics, train.py:173), and
+    # a resumed run gets its moments and step count back (train.py:256).
+    state = TrainStep(model, StepConfig.from_args(args), world_size=args.world_size)
+    model._dvla_train_step = state
+    if opt_state is not None:
+        if opt_state.get("format") != "dvla_flat_adamw_v1":
+            raise SystemExit("optimizer_state_dict is not in this package's flat-AdamW format (a torch.optim.AdamW state from "
+                             "the reference cannot be mapped: it is index-keyed over a different parameter list)")
+        state.flat.load_optimizer_state_dict(opt_state)
     ckpt_dir = os.path.join(f"{args.save_checkpoint_path}", args.run_name)
     if args.rank == 0 and args.save_checkpoint:
         os.makedirs(ckpt_dir, exist_ok=True)
@@ -157,11 +205,11 @@ def main(args, loader=None):
         state = train_one_epoch_calvin(args=args, model=ddp_model, epoch=epoch, optimizer=None, lr_scheduler=sched,
                                        calvin_loader=loader, device_id=device_id, wandb=None)
         if args.rank == 0 and args.save_checkpoint and epoch % args.save_checkpoint_seq == 0 and epoch > args.start_save_checkpoint:
-            opt_sd = {"m": state.flat.m.cpu(), "v": state.flat.v.cpu(), "step": state.flat.step_count.cpu(), "names": state.flat.names}
-            torch.save({"epoch": epoch, "model_state_dict": get_checkpoint(ddp_model), "optimizer_state_dict": opt_sd,
+            torch.save({"epoch": epoch, "model_state_dict": get_checkpoint(ddp_model),
+                        "optimizer_state_dict": state.flat.optimizer_state_dict(),
                         "lr_scheduler_state_dict": sched.state_dict()}, os.path.join(ckpt_dir, f"{epoch}.pth"))
     if args.rank == 0 and state is not None:
-        print(f"[train] done: {state.micro} micro-steps, last loss terms "
+        print(f"[train] done: {state.total_micro} micro-steps, last loss terms "
               f"{ {k: round(float(v), 5) for k, v in state.last_terms.items()} }")
     return state
 

@@ -372,6 +372,151 @@ class DreamVLA(nn.Module):
             self.action_decoder_type = next(self.action_decoder.parameters()).type()
 
     # ------------------------------------------------------------------------------------------------------------------
+    def _encode_state(self, st):
+        """reference :656-664.  st [n, 7] (arm 6 + open/closed flag) or [n, 8] (--gripper_width) -> [n, D]."""
+        dt = torch.bfloat16
+        st = st.to(dt)
+        arm_state_feature = self.arm_state_encoder(st[:, :6].contiguous())
+        if not self.gripper_width:
+            idx = (st[:, 6:].flatten() >= 1).long()      # 0 if < 1 else 1 (no host scalars: graph-capturable)
+            idxf = idx.to(dt)
+            gripper_in = torch.stack((1 - idxf, idxf), dim=1)      # == F.one_hot(idx, 2), without its value check
+        else:
+            gripper_in = st[:, 6:].contiguous()
+        gripper_state_feature = self.gripper_state_encoder(gripper_in)
+        return self.state_projector(torch.cat((arm_state_feature, gripper_state_feature), dim=1))
+
+    def _encode_vision(self, image_primary, image_wrist):
+        """reference :666-673, :716-737 for n frames of both cameras in ONE ViT / resampler batch.
+        [n, 3, 224, 224] x2 -> (primary tokens [n, nq, D], wrist tokens [n, nq, D], cls_primary [n, 1, D], cls_wrist [n, 1, D])."""
+        dt = torch.bfloat16
+        n = image_primary.shape[0]
+        D = self.hidden_dim
+        with torch.no_grad():
+            imgs = torch.cat((image_primary, image_wrist), dim=0).to(dt)
+            feats, _, _ = self.vision_encoder.forward_encoder(imgs, mask_ratio=0.0)        # [2n, 197, 768]
+        cls_tok = feats[:, 0, :]                                                            # [2n, 768]
+        patches = feats[:, 1:, :]                                                           # [2n, 196, 768]
+        resampled = self.perceiver_resampler(patches.unsqueeze(1).unsqueeze(1))            # [2n, 1, nq, 768]
+        resampled = resampled.reshape(2, n * self.NUM_RESAMPLER_QUERY, 768)
+        pe = self.image_primary_projector(resampled[0]).view(n, -1, D)
+        we = self.image_wrist_projector(resampled[1]).view(n, -1, D)
+        cp = self.cls_token_primary_projector(cls_tok[:n].contiguous()).view(n, 1, D)
+        cw = self.cls_token_wrist_projector(cls_tok[n:].contiguous()).view(n, 1, D)
+        return pe, we, cp, cw
+
+    def _query_tokens(self):
+        """The learned B-slot tokens of one timestep, in slot order (:745-757): obs, depth, dino, sam, traj, action."""
+        parts = []
+        if self.obs_pred:
+            parts.append(self.obs_tokens)
+        if not self.share_query:
+            if self.depth_pred:
+                parts.append(self.depth_tokens)
+            if self.dino_feat_pred:
+                parts.append(self.dino_feat_tokens)
+            if self.sam_feat_pred:
+                parts.append(self.sam_feat_tokens)
+            if self.trajectory_pred:
+                parts.append(self.trajectory_tokens)
+        if self.action_pred_steps > 0:
+            parts.append(self.action_pred_token)
+        return parts
+
+    def _ddim_actions(self, feat, sample_noise, dev):
+        """10-step DDIM with classifier-free guidance 1.5 (:935-987) on feat [n, action_pred_steps, D] -> [n, steps, 7]."""
+        bs = feat.shape[0]
+        cfg_scale = 1.5
+        if sample_noise is None:
+            sample_noise = torch.randn(bs, self.action_pred_steps, self.action_model.in_channels, device=dev)
+        noise = sample_noise.to(feat.dtype)
+        noise = torch.cat([noise, noise], 0)
+        uncondition = self.action_model.net.z_embedder.uncondition.unsqueeze(0).expand(bs, self.action_pred_steps, -1)
+        z = torch.cat([feat, uncondition], 0)
+        if self.action_model.ddim_diffusion is None:
+            self.action_model.create_ddim(ddim_step=10)
+        samples = self.action_model.ddim_diffusion.ddim_sample_loop(
+            self.action_model.net.forward_with_cfg, noise.shape, noise, clip_denoised=False,
+            model_kwargs=dict(z=z, cfg_scale=cfg_scale), device=dev, eta=0.0)
+        samples, _ = samples.chunk(2, dim=0)
+        return samples
+
+    # ---- rollout-level incremental inference (SURVEY §8 f-1; reference utils/eval_utils_calvin.py:82-147) --------------
+    @torch.no_grad()
+    def encode_text_embedding(self, text_token):
+        """text_token int [n, 77] -> projected text slot [n, D] (:643-653).  Frozen for an episode by the rollout wrapper."""
+        tf = self.clip_model.encode_text(text_token.contiguous()).to(torch.bfloat16)
+        return self.text_projector(tf)
+
+    @torch.no_grad()
+    def encode_frame_tokens(self, image_primary, image_wrist, state):
+        """Per-frame, position-independent slots of n frames: [state(1) . primary nq . wrist nq . cls_p . cls_w] -> [n, 35, D].
+        A frame's block depends on that frame only (ViT, resampler and projectors never mix frames), so a rollout can keep
+        it across env steps instead of re-encoding the whole window (the reference re-runs all S frames every step)."""
+        st = self._encode_state(state).unsqueeze(1)
+        pe, we, cp, cw = self._encode_vision(image_primary, image_wrist)
+        return torch.cat((st, pe, we, cp, cw), dim=1)
+
+    def _rollout_mask(self, sel, prune, device):
+        """AttnMask of the tokens kept for selected timestep `sel`.  prune=False: the full [L, L] mask.  prune=True: the slots
+        of timestep `sel` plus, transitively, every slot one of the kept rows can see -- for the finetune / evaluate masks
+        that is the A slots of timesteps 0..sel and the B slots of `sel` (later timesteps are hidden by :41, B slots of other
+        timesteps by :44).  A dropped token is visible to no kept row, so the kept rows' attention is unchanged."""
+        if not prune:
+            return self._attn_mask(device), None, None
+        key = (self.attention_mask.data_ptr(), self.attention_mask._version, sel, str(device))
+        cache = self.__dict__.setdefault("_rollout_mask_cache", {})
+        if key not in cache:
+            n_tok = self.attention_mask.shape[0] // self.sequence_length
+            vis = (self.attention_mask.detach().float().cpu() == 0)
+            keep = torch.zeros(vis.shape[0], dtype=torch.bool)
+            keep[sel * n_tok:(sel + 1) * n_tok] = True               # every slot of the selected timestep
+            while True:                                              # + everything a kept row can see (transitively)
+                grown = keep | vis[keep].any(dim=0)
+                if bool((grown == keep).all()):
+                    break
+                keep = grown
+            idx = keep.nonzero().flatten()
+            cache[key] = (ops.AttnMask.from_additive(self.attention_mask.detach().float().cpu()[idx][:, idx].contiguous(),
+                                                     device), idx.to(device), idx)
+        return cache[key]
+
+    @torch.no_grad()
+    def rollout_action(self, text_embedding, frame_tokens, sel, sample_noise=None, prune=True):
+        """One action for the timestep `sel` of a window (mode='test' of `forward`, restricted to what that action needs).
+
+        text_embedding [1, D] (encode_text_embedding), frame_tokens [S, 35, D] (encode_frame_tokens; frames after `sel`
+        are the padded repeats of the reference wrapper and are ignored when prune=True).  Returns (arm [1, steps, 6],
+        gripper [1, steps, 1]) == rows `sel` of the full-window outputs.
+          prune=False: the backbone sees exactly the full window's L tokens (bit-identical activations for row `sel`);
+          prune=True:  tokens that no kept row can attend to are dropped before the backbone (L=930 -> 36*(sel+1)+57 at the
+                       eval.sh configuration); same mathematics, different KV tiling => equal up to bf16 rounding.
+        The DiT / DDIM sampler only runs for the selected timestep (the reference samples all S and discards S-1)."""
+        assert self.use_dit_head and self.action_pred_steps > 0
+        S, D = self.sequence_length, self.hidden_dim
+        dev = frame_tokens.device
+        n_a = 1 + 1 + 2 * self.NUM_RESAMPLER_QUERY + 2
+        q = torch.cat([t.reshape(-1, D) for t in self._query_tokens()], dim=0)                    # [n_b, D]
+        n_b = q.shape[0]
+        pos = self.transformer_backbone_position_embedding.view(S, 1, D)
+        a_tok = torch.cat((text_embedding.view(1, 1, D).expand(S, 1, D), frame_tokens), dim=1)   # [S, 36, D]
+        mask, idx, idx_host = self._rollout_mask(sel, prune, dev)
+        full = (torch.cat((a_tok, q.unsqueeze(0).expand(S, n_b, D)), dim=1) + pos).reshape(S * (n_a + n_b), D)
+        a0 = sel * (n_a + n_b) + n_a + n_b - self.action_pred_steps      # first action row of the selected timestep
+        if prune:
+            x = full.index_select(0, idx).unsqueeze(0)                   # kept tokens, original order
+            r0 = int((idx_host < a0).sum())                                 # the action rows are kept: their new position
+            act_rows = slice(r0, r0 + self.action_pred_steps)
+        else:
+            x = full.unsqueeze(0)
+            act_rows = slice(a0, a0 + self.action_pred_steps)
+        x = self.embedding_layer_norm(x.contiguous())
+        h = self.transformer_backbone(inputs_embeds=x, attention_mask=mask)
+        feat = h[:, act_rows, :].contiguous()                                                   # [1, steps, D]
+        samples = self._ddim_actions(feat, sample_noise, dev)
+        return samples[..., :6], samples[..., 6:]
+
+    # ------------------------------------------------------------------------------------------------------------------
     def forward(self, image_primary, image_wrist, state, text_token, action=None, track_infos=None, action_label=None,
                 mode="train", diffusion_noise=None, diffusion_timestep=None, diffusion_drop_ids=None, sample_noise=None):
         """Reference :609-991.  The four trailing keyword arguments inject the tensors the reference samples inside
@@ -396,31 +541,11 @@ class DreamVLA(nn.Module):
                 text_feature = self.clip_model.encode_text(text_token.flatten(0, 1)).to(dt)
         text_embedding = self.text_projector(text_feature).view(B, S, -1, D)
 
-        # ---- state (:656-664) ----
-        st = state.flatten(0, 1).to(dt)
-        arm_state_feature = self.arm_state_encoder(st[:, :6].contiguous())
-        if not self.gripper_width:
-            idx = (st[:, 6:].flatten() >= 1).long()      # 0 if < 1 else 1 (no host scalars: graph-capturable)
-            idxf = idx.to(dt)
-            gripper_in = torch.stack((1 - idxf, idxf), dim=1)      # == F.one_hot(idx, 2), without its value check
-        else:
-            gripper_in = st[:, 6:].contiguous()
-        gripper_state_feature = self.gripper_state_encoder(gripper_in)
-        state_embedding = self.state_projector(torch.cat((arm_state_feature, gripper_state_feature), dim=1)).view(B, S, -1, D)
-
-        # ---- vision: both cameras in one batch (:666-673) ----
-        with torch.no_grad():
-            imgs = torch.cat((image_primary.flatten(0, 1), image_wrist.flatten(0, 1)), dim=0).to(dt)
-            feats, _, _ = self.vision_encoder.forward_encoder(imgs, mask_ratio=0.0)        # [2BS, 197, 768]
-        n = B * S
-        cls_tok = feats[:, 0, :]                                                            # [2BS, 768]
-        patches = feats[:, 1:, :]                                                           # [2BS, 196, 768]
-        resampled = self.perceiver_resampler(patches.unsqueeze(1).unsqueeze(1))            # [2BS, 1, nq, 768]
-        resampled = resampled.reshape(2, n * self.NUM_RESAMPLER_QUERY, 768)
-        image_primary_embedding = self.image_primary_projector(resampled[0]).view(B, S, -1, D)
-        image_wrist_embedding = self.image_wrist_projector(resampled[1]).view(B, S, -1, D)
-        cls_p = self.cls_token_primary_projector(cls_tok[:n].contiguous()).view(B, S, -1, D)
-        cls_w = self.cls_token_wrist_projector(cls_tok[n:].contiguous()).view(B, S, -1, D)
+        # ---- state (:656-664) and vision: both cameras in one batch (:666-673, :716-737) ----
+        state_embedding = self._encode_state(state.flatten(0, 1)).view(B, S, -1, D)
+        pe, we, cp, cw = self._encode_vision(image_primary.flatten(0, 1), image_wrist.flatten(0, 1))
+        image_primary_embedding, image_wrist_embedding = pe.view(B, S, -1, D), we.view(B, S, -1, D)
+        cls_p, cls_w = cp.view(B, S, -1, D), cw.view(B, S, -1, D)
 
         # ---- token assembly (:739-759); slot order is part of the contract ----
         parts = [text_embedding, state_embedding, image_primary_embedding, image_wrist_embedding, cls_p, cls_w]
@@ -531,21 +656,7 @@ class DreamVLA(nn.Module):
                                                          force_drop_ids=diffusion_drop_ids)
                 gripper_pred_action = arm_pred_action
             else:  # mode == 'test': 10-step DDIM with classifier-free guidance 1.5 (:935-987)
-                bs = B * S
-                feat = action_pred_feature.flatten(0, 1)
-                cfg_scale = 1.5
-                if sample_noise is None:
-                    sample_noise = torch.randn(bs, self.action_pred_steps, self.action_model.in_channels, device=dev)
-                noise = sample_noise.to(feat.dtype)
-                noise = torch.cat([noise, noise], 0)
-                uncondition = self.action_model.net.z_embedder.uncondition.unsqueeze(0).expand(bs, self.action_pred_steps, -1)
-                z = torch.cat([feat, uncondition], 0)
-                if self.action_model.ddim_diffusion is None:
-                    self.action_model.create_ddim(ddim_step=10)
-                samples = self.action_model.ddim_diffusion.ddim_sample_loop(
-                    self.action_model.net.forward_with_cfg, noise.shape, noise, clip_denoised=False,
-                    model_kwargs=dict(z=z, cfg_scale=cfg_scale), device=dev, eta=0.0)
-                samples, _ = samples.chunk(2, dim=0)
+                samples = self._ddim_actions(action_pred_feature.flatten(0, 1), sample_noise, dev)
                 arm_pred_action, gripper_pred_action = samples.unsqueeze(0)[..., :6], samples.unsqueeze(0)[..., 6:]
         return (arm_pred_action, gripper_pred_action, image_pred, arm_pred_state, gripper_pred_state, loss_arm_action,
                 depth_pred, traj_pred, dino_pred, sam_pred)

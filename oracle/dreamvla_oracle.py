@@ -37,7 +37,9 @@ def _mha(q, k, v, scale, mask=None):
     s = torch.matmul(q, k.transpose(-1, -2)) * scale
     if mask is not None:
         s = s + mask
-    p = torch.softmax(s, dim=-1)
+    # softmax in fp32, probabilities back in the value dtype (what SDPA / HF eager attention do under --precision bf16;
+    # a no-op for the fp32 oracle)
+    p = torch.softmax(s.float(), dim=-1).to(v.dtype)
     o = torch.matmul(p, v).permute(0, 2, 1, 3)
     return o.reshape(o.shape[0], o.shape[1], -1)
 

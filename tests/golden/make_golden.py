@@ -140,6 +140,6 @@ def run_case(name, cfg):
 if __name__ == "__main__":
     torch.set_num_threads(8)
     only = sys.argv[1:]
-    for name, cfg in {**synth.CASES, **synth.CPU_ONLY_CASES}.items():
+    for name, cfg in {**synth.CASES, **synth.CPU_ONLY_CASES, **synth.FULL_CASES}.items():
         if not only or name in only:
             run_case(name, cfg)

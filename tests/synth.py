@@ -34,6 +34,18 @@ CPU_ONLY_CASES = {
                                  sam_feat_pred=False, use_dit_head=True, sequence_length=3, gripper_width=True),
 }
 
+# Full-depth cases: BASELINE.json's C2 (CALVIN, 24 layers, S=10, five world heads + DiT, L=1290) and C3 (LIBERO, S=7,
+# --gripper_width, world heads off, L=273) at batch 1.  GPU parity only (tests/test_full_depth_gpu.py); the reference runs
+# them on the CPU in fp32 in ~1 min each when the goldens are generated.
+FULL_CASES = {
+    "calvin_full": dict(BASE, obs_pred=True, depth_pred=True, trajectory_pred=True, dino_feat_pred=True, sam_feat_pred=True,
+                        use_dit_head=True, transformer_layers=24, sequence_length=10, weight_seed=21, input_seed=22,
+                        draw_seed=23),
+    "libero_full": dict(BASE, obs_pred=False, depth_pred=False, trajectory_pred=False, dino_feat_pred=False,
+                        sam_feat_pred=False, use_dit_head=True, transformer_layers=24, sequence_length=7, gripper_width=True,
+                        weight_seed=31, input_seed=32, draw_seed=33),
+}
+
 CTOR_KEYS = ("sequence_length", "num_resampler_query", "num_obs_token_per_image", "obs_pred", "atten_only_obs",
              "attn_robot_proprio_state", "atten_goal", "atten_goal_state", "mask_l_obs_ratio", "action_pred_steps",
              "transformer_layers", "hidden_dim", "transformer_heads", "phase", "gripper_width", "pred_num", "depth_pred",

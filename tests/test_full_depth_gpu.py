@@ -1,0 +1,187 @@
+"""Full-depth parity on the GPU at BASELINE.json's real shapes: C2 (CALVIN, 24 layers, S=10, five world heads + DiT,
+L=1290) and C3 (LIBERO, 24 layers, S=7, --gripper_width, L=273), batch 1.
+
+Three things are compared against the goldens recorded from the UNMODIFIED reference (fp32, CPU, tests/golden/make_golden.py)
+and against the fp32 oracle run on the same GPU (oracle/, pinned to those goldens):
+
+  err_ours      rel-L2 of this package's CUDA path (bf16 storage, fp32 accumulate)
+  err_ref_bf16  rel-L2 of a reference-style bf16 execution: the oracle's restatement with bf16 weights / inputs under
+                torch.autocast(bf16), i.e. what `--precision bf16` makes of the reference on torch's own kernels
+
+The bar: err_ours <= err_ref_bf16 + 1e-3 for every output tensor, loss term and probed
+gradient -- "no worse than the reference's own bf16 path".  All achieved errors are printed (pytest -s / captured log).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+SLACK = 1e-3
+
+PROBE = ["transformer_backbone.h.0.attn.c_attn.weight", "transformer_backbone.h.11.mlp.c_fc.weight",
+         "transformer_backbone.h.23.mlp.c_proj.weight", "transformer_backbone.h.0.ln_1.weight",
+         "transformer_backbone.h.12.attn.c_proj.bias", "transformer_backbone.ln_f.weight",
+         "perceiver_resampler.layers.0.0.to_kv.weight", "perceiver_resampler.layers.2.1.1.weight", "perceiver_resampler.latents",
+         "image_primary_projector.weight", "cls_token_wrist_projector.weight", "text_projector.weight", "state_projector.weight",
+         "arm_state_encoder.weight", "embedding_layer_norm.weight", "transformer_backbone_position_embedding",
+         "action_pred_token", "action_model.net.blocks.0.attn.qkv.weight", "action_model.net.blocks.11.mlp.fc2.weight",
+         "action_model.net.final_layer.linear.weight", "action_model.net.z_embedder.linear.weight",
+         "action_model.net.x_embedder.linear.weight"]
+PROBE_HEADS = ["image_decoder.0.attn.qkv.weight", "image_decoder_pred.weight", "depth_decoder.1.mlp.fc2.weight",
+               "dino_decoder_pred.weight", "dino_feat_decoder.1.attn.proj.weight", "sam_feat_decoder.0.norm1.weight",
+               "sam_decoder_obs_pred_projector.weight", "traj_decoder_obs_pred_projector.bias", "traj_decoder.0.mlp.fc1.weight",
+               "obs_tokens", "depth_tokens", "mask_token", "dino_mask_token"]
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    return torch.device("cuda:0")
+
+
+def build_ours(cfg, dev, depth_bias=0.0):
+    from dreamvla_b200.models import DreamVLA
+    torch.manual_seed(0)
+    m = DreamVLA(finetune_type="calvin", clip_device="cpu", vit_checkpoint_path=None, **synth.ctor_kwargs(cfg))
+    sd = synth.synth_state_dict(m.state_dict(), cfg["weight_seed"])
+    if depth_bias and "depth_decoder_pred.bias" in sd:
+        sd["depth_decoder_pred.bias"] = sd["depth_decoder_pred.bias"] + depth_bias
+    m.load_state_dict(sd)
+    m = m.bfloat16().to(dev)
+    m._init_model_type()
+    gp = m.transformer_backbone
+    gp.embd_pdrop = 0.0
+    for blk in gp.h:
+        blk.attn.attn_pdrop = blk.attn.resid_pdrop = blk.mlp.resid_pdrop = 0.0
+    return m, sd
+
+
+def oracle_run(sd, cfg, inp, gold, dev, dtype, labels=None, mode="train", grads=None):
+    """The oracle on the GPU: dtype float32 = the checker; bfloat16 = reference-style bf16 execution (bf16 weights and inputs
+    under autocast).  Returns (forward dict, loss dict or None, {name: grad} or None)."""
+    from oracle import dreamvla_oracle as O
+    frozen = ("vision_encoder.", "clip_model.", "attention_mask", "position_embedding")
+    osd = {}
+    for k, v in sd.items():
+        t = v.to(dev)
+        if t.is_floating_point():
+            t = t.to(dtype)
+            if grads is not None and (not any(f in k for f in frozen) or k == "transformer_backbone_position_embedding"):
+                t.requires_grad_(True)
+        osd[k] = t
+    cast = lambda t: t.to(dev, dtype) if t.is_floating_point() else t.to(dev)     # noqa: E731
+    i = {k: cast(v) for k, v in inp.items()}
+    kw = {}
+    if mode == "train" and cfg["use_dit_head"]:
+        kw = dict(action_label=i["action_label"], diffusion_noise=cast(gold["diffusion_noise"]),
+                  diffusion_timestep=gold["diffusion_timestep"].to(dev), diffusion_drop_ids=gold["diffusion_drop_ids"].to(dev))
+    if mode == "test":
+        kw = dict(sample_noise=cast(gold["sample_noise"]))
+    with torch.set_grad_enabled(grads is not None), torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+        fwd = O.dreamvla_forward(osd, cfg, i["image_primary"], i["image_wrist"], i["state"], i["text_token"], mode=mode, **kw)
+        losses = None
+        if labels is not None:
+            losses = O.train_losses(dict(cfg, future_steps=3, flow_as_mask=True), fwd, {k: cast(v) for k, v in labels.items()})
+        elif grads is not None:
+            losses = {"loss": fwd["loss_action"], "loss_action": fwd["loss_action"]}
+    g = None
+    if grads is not None:
+        losses["loss"].float().backward()
+        g = {k: osd[k].grad for k in grads}
+    return fwd, losses, g
+
+
+def check(table, bad, what, e_ours, e_ref):
+    table.append(f"  {what:58s} err_ours {e_ours:.3e}   err_ref_bf16 {e_ref:.3e}   margin {e_ref + SLACK - e_ours:+.2e}")
+    if not e_ours <= e_ref + SLACK:
+        bad.append(what)
+
+
+@pytest.mark.parametrize("name", list(synth.FULL_CASES))
+def test_full_depth_forward_losses_gradients(name, dev):
+    from dreamvla_b200.utils.train_utils import StepConfig, build_labels, compute_losses
+    cfg = synth.FULL_CASES[name]
+    fx = json.load(open(os.path.join(GOLDEN, f"{name}.json")))
+    gold = torch.load(os.path.join(GOLDEN, f"{name}.pt"))
+    table, bad = [f"[{name}] 24 layers, S={cfg['sequence_length']}, B=1"], []
+    m, sd = build_ours(cfg, dev)
+    inp = synth.synth_inputs(cfg)
+    dinp = {k: v.to(dev) for k, v in inp.items()}
+    # ---- bit-exact contracts ----
+    vis = (m.attention_mask.float().cpu() == 0)
+    assert torch.equal(torch.from_numpy(np.packbits(vis.numpy(), axis=1)), gold["mask_packed"])
+    assert int(vis.sum()) == fx["mask_visible_pairs"]
+    # ---- forward (train mode, golden draws) ----
+    m.train()
+    draws = dict(diffusion_noise=gold["diffusion_noise"].to(dev), diffusion_timestep=gold["diffusion_timestep"].to(dev),
+                 diffusion_drop_ids=gold["diffusion_drop_ids"].to(dev).long())
+    with torch.no_grad():
+        out = m(dinp["image_primary"], dinp["image_wrist"], dinp["state"], dinp["text_token"], action_label=dinp["action_label"], **draws)
+    f32, _, _ = oracle_run(sd, cfg, inp, gold, dev, torch.float32)
+    f16, _, _ = oracle_run(sd, cfg, inp, gold, dev, torch.bfloat16)
+    names = ["arm", "gripper", "image_pred", None, None, None, "depth_pred", "traj_pred", "dino_pred", "sam_pred"]
+    for nm, o in zip(names, out):
+        if nm and nm.endswith("_pred") and o is not None:
+            assert list(o.shape) == fx[nm + "_shape"]
+            g = gold[nm + "_sub"]
+            assert rel(synth.subsample(f32[nm]), g) < 1e-4, f"GPU fp32 oracle drifted from the reference golden on {nm}"
+            check(table, bad, f"forward {nm} (vs reference golden)", rel(synth.subsample(o), g), rel(synth.subsample(f16[nm]), g))
+    la = fx["loss_action"]
+    assert abs(float(f32["loss_action"]) - la) < 1e-4 * abs(la)
+    check(table, bad, "DiT loss (vs reference golden)", abs(float(out[0]) - la) / abs(la), abs(float(f16["loss_action"]) - la) / abs(la))
+    # ---- test mode: 10-step DDIM, CFG 1.5 ----
+    m.eval()
+    with torch.no_grad():
+        ot = m(dinp["image_primary"], dinp["image_wrist"], dinp["state"], dinp["text_token"], mode="test",
+               sample_noise=gold["sample_noise"].to(dev))
+    t16, _, _ = oracle_run(sd, cfg, inp, gold, dev, torch.bfloat16, mode="test")
+    check(table, bad, "DDIM arm actions (vs reference golden)", rel(ot[0], gold["test_arm"]), rel(t16["arm_pred_action"], gold["test_arm"]))
+    check(table, bad, "DDIM gripper actions (vs reference golden)", rel(ot[1], gold["test_gripper"]),
+          rel(t16["gripper_pred_action"], gold["test_gripper"]))
+    del f32, f16, t16, out, ot
+    # ---- losses + gradients (depth head shifted positive so that SiLog is well conditioned, see test_model_gpu.py) ----
+    all_heads = cfg["obs_pred"]
+    del m
+    m, sdg = build_ours(cfg, dev, depth_bias=6.0 if all_heads else 0.0)
+    m.train()
+    S = cfg["sequence_length"]
+    lab = {k: v.to(torch.bfloat16).float() for k, v in synth.synth_labels(cfg).items()} if all_heads else None
+    scfg = StepConfig(sequence_length=S, future_steps=3, use_dit_head=True, loss_image=all_heads, loss_depth=all_heads,
+                      loss_dino_feat=all_heads, loss_sam_feat=all_heads, loss_trajectory=all_heads, flow_as_mask=all_heads,
+                      gripper_width=bool(cfg.get("gripper_width", False)))
+    out = m(dinp["image_primary"], dinp["image_wrist"], dinp["state"], dinp["text_token"], action_label=dinp["action_label"], **draws)
+    labels = build_labels(scfg, {k: v.to(dev, torch.bfloat16) for k, v in (lab or {}).items()},
+                          dict(image=all_heads, depth=all_heads, dino=all_heads, sam=all_heads, traj=all_heads))
+    terms = compute_losses(scfg, out, labels, bs=cfg["batch"])
+    total = sum(terms.values())
+    total.backward()
+    probe = PROBE + (PROBE_HEADS if all_heads else [])
+    assert len(probe) >= 20
+    _, l32, g32 = oracle_run(sdg, cfg, inp, gold, dev, torch.float32, labels=lab, grads=probe)
+    _, l16, g16 = oracle_run(sdg, cfg, inp, gold, dev, torch.bfloat16, labels=lab, grads=probe)
+    check(table, bad, "total train loss (vs fp32 oracle)", abs(float(total) - float(l32["loss"])) / abs(float(l32["loss"])),
+          abs(float(l16["loss"]) - float(l32["loss"])) / abs(float(l32["loss"])))
+    if all_heads:
+        for mine, theirs, w in (("image", "loss_image", 0.1), ("depth", "loss_depth", 0.001), ("dino", "loss_dino", 0.01),
+                                ("sam", "loss_sam", 0.01), ("traj", "loss_traj", 0.1)):
+            ref = w * float(l32[theirs])
+            check(table, bad, f"loss term {mine} (vs fp32 oracle)", abs(float(terms[mine]) - ref) / abs(ref),
+                  abs(w * float(l16[theirs]) - ref) / abs(ref))
+    params = dict(m.named_parameters())
+    for k in probe:
+        assert params[k].grad is not None and g32[k] is not None, k
+        check(table, bad, f"grad {k}", rel(params[k].grad, g32[k]), rel(g16[k], g32[k]))
+    print("\n".join(table))
+    assert not bad, "worse than the reference-style bf16 path + 1e-3 on: " + ", ".join(bad) + "\n" + "\n".join(table)

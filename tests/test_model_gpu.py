@@ -45,10 +45,10 @@ def dev():
     return torch.device("cuda:0")
 
 
-@pytest.mark.parametrize("name", list(synth.CASES))
+@pytest.mark.parametrize("name", list(synth.CASES) + list(synth.CPU_ONLY_CASES))
 def test_forward_matches_oracle_and_golden(name, dev):
     from oracle import dreamvla_oracle as O
-    cfg = synth.CASES[name]
+    cfg = {**synth.CASES, **synth.CPU_ONLY_CASES}[name]
     fx = json.load(open(os.path.join(GOLDEN, f"{name}.json")))
     gold = torch.load(os.path.join(GOLDEN, f"{name}.pt"))
     model, sd = build(cfg, dev)

@@ -582,16 +582,23 @@ static bool strides_ok(const void* ptr, long long sb, long long ss, long long sh
   return ptr && (reinterpret_cast<uintptr_t>(ptr) % 16 == 0) && sb % 8 == 0 && ss % 8 == 0 && sh % 8 == 0;
 }
 
-int attn_fwd_tc_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s);   // attention_tc.cu (tcgen05 / TMEM, single-role CTA)
+bool attn_small_applicable(int64_t Lq, int64_t Lk, const void* mask, float dropout_p);   // attention_small.cu
+int attn_small_fwd_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s);
+int attn_small_bwd_dispatch(const dvla_attn_bwd_args* a, cudaStream_t s);
+static bool attn_small_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("DVLA_ATTN_SMALL"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1;
+}
 int attn_fwd_ws_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s, long long q_rows);   // attention_fwd_ws.cu (tcgen05, warp-specialised)
 
-// 0 = auto (warp-specialised tcgen05 kernel for Lq >= 96, mma.sync kernel for short query blocks), 1 = mma.sync,
-// 2 = single-role tcgen05 kernel (attention_tc.cu), 3 = warp-specialised tcgen05 kernel whenever expressible
+// 0 = auto (warp-specialised tcgen05 kernel for Lq >= 96, SIMT row kernel for Lq <= 32 without mask / dropout, mma.sync
+// kernel otherwise), 1 = mma.sync everywhere, 3 = warp-specialised tcgen05 kernel whenever expressible
 static int attn_fwd_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("DVLA_ATTN_FWD");
-    mode = (e && !strcmp(e, "legacy")) ? 1 : (e && !strcmp(e, "tc")) ? 2 : (e && !strcmp(e, "ws")) ? 3 : 0;
+    mode = (e && !strcmp(e, "legacy")) ? 1 : (e && !strcmp(e, "ws")) ? 3 : 0;
   }
   return mode;
 }
@@ -608,10 +615,8 @@ int attn_fwd_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s) {
   if (a->mask && a->mask_words * 32 < a->Lk) { set_error("attn_fwd: mask_words too small"); return DVLA_ERR_INVALID; }
   if (a->mask && !a->tile_flags) { set_error("attn_fwd: mask given without tile_flags"); return DVLA_ERR_INVALID; }
   const int mode = attn_fwd_mode();
-  if (mode == 2) {   // the single-role tcgen05 forward is parity-green but slower than the mma.sync kernel: opt-in
-    const int rc = attn_fwd_tc_dispatch(a, s);
-    if (rc != DVLA_ERR_UNSUPPORTED) return rc;      // strides a tensor map cannot express -> mma.sync kernel below
-  }
+  if (mode == 0 && attn_small_enabled() && attn_small_applicable(a->Lq, a->Lk, a->mask, a->dropout_p))
+    return attn_small_fwd_dispatch(a, s);
   AttnParams p;
   memset(&p, 0, sizeof(p));
   p.q = (const bf16*)a->q; p.k = (const bf16*)a->k; p.v = (const bf16*)a->v; p.out = (bf16*)a->o; p.lse = a->lse;
@@ -638,18 +643,16 @@ int attn_fwd_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s) {
   return DVLA_OK;
 }
 
-int attn_bwd_tc_dispatch(const dvla_attn_bwd_args* a, const uint32_t* mask_t, int mask_t_words, cudaStream_t s);  // attention_bwd_tc.cu
-int attn_bwd_pipe_dispatch(const dvla_attn_bwd_args* a, const uint32_t* mask_t, int mask_t_words, cudaStream_t s);  // attention_bwd_pipe.cu
 int attn_bwd_ws_dispatch(const dvla_attn_bwd_args* a, const uint32_t* mask_t, int mask_t_words, cudaStream_t s, long long q_rows,
                          long long k_rows);    // attention_bwd_ws.cu
 
-// 0 = auto (warp-specialised tcgen05 kernels when both sequences are >= 96 long), 1 = mma.sync kernels,
-// 2 = single-role tcgen05 kernels (attention_bwd_tc.cu), 3 = attention_bwd_pipe.cu, 4 = warp-specialised whenever expressible
+// 0 = auto (warp-specialised tcgen05 kernels when both sequences are >= 96 long, SIMT row kernels for Lq <= 32 without
+// mask / dropout, mma.sync kernels otherwise), 1 = mma.sync kernels everywhere, 4 = warp-specialised whenever expressible
 static int attn_bwd_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("DVLA_ATTN_BWD");
-    mode = (e && !strcmp(e, "legacy")) ? 1 : (e && !strcmp(e, "tc")) ? 2 : (e && !strcmp(e, "pipe")) ? 3 : (e && !strcmp(e, "ws")) ? 4 : 0;
+    mode = (e && !strcmp(e, "legacy")) ? 1 : (e && !strcmp(e, "ws")) ? 4 : 0;
   }
   return mode;
 }
@@ -686,21 +689,15 @@ int attn_bwd_dispatch(const dvla_attn_bwd_args* a, cudaStream_t s) {
     p.drop_seed = a->dropout_seed;
     p.drop_seed_ptr = a->dropout_seed_ptr;
   }
+  const int bmode = attn_bwd_mode();
+  if (bmode == 0 && attn_small_enabled() && attn_small_applicable(a->Lq, a->Lk, a->mask, a->dropout_p))
+    return attn_small_bwd_dispatch(a, s);          // writes delta itself
   const long long rows = (long long)p.B * p.H * p.Lq;
   attn_delta_kernel<<<(unsigned)((rows * 8 + 255) / 256), 256, 0, s>>>(p);
   DVLA_CHECK_LAUNCH("attn_delta");
-  const int bmode = attn_bwd_mode();
-  if (bmode == 3) {      // warp-specialised pipelined tcgen05 kernels
-    const int rc = attn_bwd_pipe_dispatch(a, a->mask_t, a->mask_t_words, s);
-    if (rc != DVLA_ERR_UNSUPPORTED) return rc;
-  }
   if (bmode == 4 || (bmode == 0 && a->Lq >= 96 && a->Lk >= 96)) {
     // warp-specialised tcgen05 kernels, 2 CTAs / SM (attention_bwd_ws.cu)
     const int rc = attn_bwd_ws_dispatch(a, a->mask_t, a->mask_t_words, s, a->Lq, a->Lk);
-    if (rc != DVLA_ERR_UNSUPPORTED) return rc;
-  }
-  if (bmode == 2) {
-    const int rc = attn_bwd_tc_dispatch(a, a->mask_t, a->mask_t_words, s);
     if (rc != DVLA_ERR_UNSUPPORTED) return rc;
   }
   attn_bwd_dkv_kernel<<<dim3(p.nkt, p.H, p.B), 128, 0, s>>>(p);

@@ -71,16 +71,82 @@ def generate_attention_mask(K, num_A, num_B, atten_goal, atten_goal_state, atten
 
 class _WorldDecoder(nn.Module):
     """Helper that RUNS one world-knowledge decoder (reference :793-911); it owns no parameters -- the parameters stay
-    on DreamVLA under the reference names."""
+    on DreamVLA under the reference names.
+
+    Reference computation per sequence: x = cat(projector(queries) [n_per], mask_token x n_mask) + pos_emb -> 2 timm Blocks
+    -> LayerNorm -> Linear on the n_mask rows.  95 % of the rows are mask tokens, and `mask_token + pos_emb[n_per:]` does not
+    depend on the sequence, which is used twice (DVLA_DECODER_ALGEBRA=0 turns both off):
+      * shared first block input: LayerNorm-1 and the QKV projection of the mask rows of block 0 are computed ONCE per call
+        ([n_mask, D] rows instead of n_seq * n_mask); the per-sequence rows are the n_per query rows only;
+      * identical mask rows: if all mask rows of pos_emb are equal (the SAM head: zero position embedding, reference
+        :414-415 / :558-564), the n_mask mask tokens of a sequence are the same vector at every depth (every layer is
+        row-wise or a softmax over the same keys), so the decoder runs on n_per + 1 rows and the attention sees the shared
+        row's key / value n_mask times; the prediction of that row is every mask row's prediction.
+    Both are identities in exact arithmetic; in bf16 only summation orders change."""
+
+    ALGEBRA = os.environ.get("DVLA_DECODER_ALGEBRA", "1") != "0"
+    _identical_cache = {}
+
+    @staticmethod
+    def _mask_rows_identical(pos_emb, n_per):
+        key = (pos_emb.data_ptr(), pos_emb._version, n_per)
+        c = _WorldDecoder._identical_cache
+        if key not in c:
+            if len(c) > 64:
+                c.clear()
+            rows = pos_emb.detach()[0, n_per:]
+            c[key] = bool((rows == rows[:1]).all().item())        # one host read per parameter version (before any capture)
+        return c[key]
+
+    @staticmethod
+    def _block_with_repeated_key(blk, x, n_per, n_rep):
+        """timm Block on x [n, n_per + 1, D] whose last row stands for n_rep identical tokens: queries are the n_per + 1
+        distinct rows, keys / values are the n_per rows plus the shared row repeated n_rep times."""
+        n, L, D = x.shape
+        at = blk.attn
+        res, h = blk.norm1.fork(x)
+        qkv = at.qkv(h).view(n, L, 3, at.num_heads, at.head_dim)
+        k = torch.cat((qkv[:, :n_per, 1], qkv[:, n_per:, 1].expand(-1, n_rep, -1, -1)), dim=1)
+        v = torch.cat((qkv[:, :n_per, 2], qkv[:, n_per:, 2].expand(-1, n_rep, -1, -1)), dim=1)
+        o = ops.attention(qkv[:, :, 0], k, v, at.scale)
+        x = at.proj(o.view(n, L, D), residual=res)
+        res, h = blk.norm2.fork(x)
+        return blk.mlp(h, residual=res)
 
     @staticmethod
     def run(feature, projector, mask_token, pos_emb, blocks, norm, pred, n_groups, n_per, n_mask, hidden, act=None):
         # feature [B, S, n_tok, D] -> projector -> [B*S*n_groups, n_per, hidden]
         B, S = feature.shape[:2]
-        emb = projector(feature.reshape(-1, feature.shape[-1])).view(B * S * n_groups, n_per, hidden)
-        mask_tokens = mask_token.expand(B * S * n_groups, n_mask, -1)
-        x = torch.cat((emb, mask_tokens), dim=1) + pos_emb
-        x = blocks(x)
+        n = B * S * n_groups
+        emb = projector(feature.reshape(-1, feature.shape[-1])).view(n, n_per, hidden)
+        if not _WorldDecoder.ALGEBRA or not all(isinstance(b.norm1, LayerNorm) for b in blocks):
+            mask_tokens = mask_token.expand(n, n_mask, -1)
+            x = torch.cat((emb, mask_tokens), dim=1) + pos_emb
+            x = blocks(x)
+            x = norm(x[:, -n_mask:, :].reshape(-1, hidden))
+            return pred(x, act=act)
+        emb = emb + pos_emb[:, :n_per]
+        if _WorldDecoder._mask_rows_identical(pos_emb, n_per):
+            m = (mask_token + pos_emb[:, n_per:n_per + 1]).expand(n, 1, hidden)
+            x = torch.cat((emb, m), dim=1)                                   # [n, n_per + 1, D]
+            for blk in blocks:
+                x = _WorldDecoder._block_with_repeated_key(blk, x, n_per, n_mask)
+            y = pred(norm(x[:, n_per, :].contiguous()), act=act)             # [n, C]: every mask row's prediction
+            return y.unsqueeze(1).expand(n, n_mask, -1)
+        # block 0 with the mask rows' LayerNorm-1 + QKV shared across sequences
+        blk = blocks[0]
+        at = blk.attn
+        m = (mask_token + pos_emb[:, n_per:])[0]                             # [n_mask, D], sequence independent
+        qkv_e = at.qkv(blk.norm1(emb))                                       # [n, n_per, 3D]
+        qkv_m = at.qkv(blk.norm1(m))                                         # [n_mask, 3D]   (once)
+        qkv = torch.cat((qkv_e, qkv_m.unsqueeze(0).expand(n, -1, -1)), dim=1).view(n, n_per + n_mask, 3, at.num_heads, at.head_dim)
+        o = ops.self_attention_fused(qkv, at.scale)
+        x = torch.cat((emb, m.unsqueeze(0).expand(n, -1, -1)), dim=1)        # the block's input (residual branch)
+        x = at.proj(o.view(n, n_per + n_mask, hidden), residual=x)
+        res, h = blk.norm2.fork(x)
+        x = blk.mlp(h, residual=res)
+        for blk in list(blocks)[1:]:
+            x = blk(x)
         x = norm(x[:, -n_mask:, :].reshape(-1, hidden))
         return pred(x, act=act)
 
@@ -429,7 +495,7 @@ class DreamVLA(nn.Module):
         cfg_scale = 1.5
         if sample_noise is None:
             sample_noise = torch.randn(bs, self.action_pred_steps, self.action_model.in_channels, device=dev)
-        noise = sample_noise.to(feat.dtype)
+        noise = sample_noise.to(device=dev, dtype=feat.dtype)
         noise = torch.cat([noise, noise], 0)
         uncondition = self.action_model.net.z_embedder.uncondition.unsqueeze(0).expand(bs, self.action_pred_steps, -1)
         z = torch.cat([feat, uncondition], 0)
@@ -548,22 +614,13 @@ class DreamVLA(nn.Module):
         cls_p, cls_w = cp.view(B, S, -1, D), cw.view(B, S, -1, D)
 
         # ---- token assembly (:739-759); slot order is part of the contract ----
-        parts = [text_embedding, state_embedding, image_primary_embedding, image_wrist_embedding, cls_p, cls_w]
-        pred_token_start_idx = 1 + 1 + 2 * self.NUM_RESAMPLER_QUERY + 2
-        if self.obs_pred:
-            parts.append(self.obs_tokens.expand(B, S, -1, -1))
-        if not self.share_query:
-            if self.depth_pred:
-                parts.append(self.depth_tokens.expand(B, S, -1, -1))
-            if self.dino_feat_pred:
-                parts.append(self.dino_feat_tokens.expand(B, S, -1, -1))
-            if self.sam_feat_pred:
-                parts.append(self.sam_feat_tokens.expand(B, S, -1, -1))
-            if self.trajectory_pred:
-                parts.append(self.trajectory_tokens.expand(B, S, -1, -1))
-        if self.action_pred_steps > 0:
-            parts.append(self.action_pred_token.expand(B, S, -1, -1))
-        transformer_input = torch.cat(parts, dim=2)
+        # per timestep: [text . state . primary nq . wrist nq . cls_p . cls_w | obs . depth . dino . sam . traj | action]
+        a_parts = [text_embedding, state_embedding, image_primary_embedding, image_wrist_embedding, cls_p, cls_w]
+        q_parts = [t.expand(B, S, -1, -1) for t in self._query_tokens()]      # query slots, action slots last
+        n_act = self.action_pred_steps if self.action_pred_steps > 0 else 0
+        n_a = 1 + 1 + 2 * self.NUM_RESAMPLER_QUERY + 2
+        n_q = sum(t.shape[2] for t in q_parts) - n_act
+        transformer_input = torch.cat(a_parts + q_parts, dim=2)
         transformer_input = transformer_input + self.transformer_backbone_position_embedding
         transformer_input = transformer_input.flatten(1, 2)
 
@@ -575,17 +632,18 @@ class DreamVLA(nn.Module):
         if marks and transformer_output.requires_grad:
             ops.on_grad_ready(transformer_output, marks["backbone_out"])
         transformer_output = transformer_output.view(B, S, -1, D)
+        q_out = transformer_output[:, :, n_a:n_a + n_q]
+        act_out = transformer_output[:, :, n_a + n_q:]
 
         # ---- world-knowledge heads (:793-911) ----
         cur = 0
         q4 = int(D / 4)
-        P0 = pred_token_start_idx
         if self.obs_pred and mode == "train":
             if self.share_query:
-                feat = transformer_output[:, :, P0:P0 + self.NUM_OBS_TOKEN, :q4]
+                feat = q_out[:, :, 0:self.NUM_OBS_TOKEN, :q4]
                 cur = 0
             else:
-                feat = transformer_output[:, :, P0:P0 + self.NUM_OBS_TOKEN, :]
+                feat = q_out[:, :, 0:self.NUM_OBS_TOKEN, :]
                 cur += self.NUM_OBS_TOKEN
             g = self.NUM_OBS_TOKEN // self.NUM_OBS_TOKEN_PER_IMAGE
             out = _WorldDecoder.run(feat, self.image_decoder_obs_pred_projector, self.mask_token,
@@ -594,10 +652,10 @@ class DreamVLA(nn.Module):
             image_pred = out.view(B * S, g, self.pred_num, self.NUM_MASK_TOKEN // self.pred_num, -1)
         if self.depth_pred and mode == "train":
             if self.share_query:
-                feat = transformer_output[:, :, P0 + cur:P0 + cur + self.NUM_DEPTH_TOKEN, q4:2 * q4]
+                feat = q_out[:, :, cur:cur + self.NUM_DEPTH_TOKEN, q4:2 * q4]
                 cur = 0
             else:
-                feat = transformer_output[:, :, P0 + cur:P0 + cur + self.NUM_DEPTH_TOKEN, :]
+                feat = q_out[:, :, cur:cur + self.NUM_DEPTH_TOKEN, :]
                 cur += self.NUM_DEPTH_TOKEN
             g = self.NUM_DEPTH_TOKEN // self.NUM_OBS_TOKEN_PER_DEPTH
             out = _WorldDecoder.run(feat, self.depth_decoder_obs_pred_projector, self.depth_mask_token,
@@ -607,10 +665,10 @@ class DreamVLA(nn.Module):
             depth_pred = out.view(B * S, g, self.pred_num, self.NUM_DEPTH_MASK_TOKEN // self.pred_num, -1)
         if self.dino_feat_pred and mode == "train":
             if self.share_query:
-                feat = transformer_output[:, :, P0 + cur:P0 + cur + self.NUM_DINO_TOKEN, 2 * q4:3 * q4]
+                feat = q_out[:, :, cur:cur + self.NUM_DINO_TOKEN, 2 * q4:3 * q4]
                 cur = 0
             else:
-                feat = transformer_output[:, :, P0 + cur:P0 + cur + self.NUM_DINO_TOKEN, :]
+                feat = q_out[:, :, cur:cur + self.NUM_DINO_TOKEN, :]
                 cur += self.NUM_DINO_TOKEN
             g = self.NUM_DINO_TOKEN // self.NUM_OBS_TOKEN_PER_DINO
             out = _WorldDecoder.run(feat, self.dino_decoder_obs_pred_projector, self.dino_mask_token,
@@ -619,10 +677,10 @@ class DreamVLA(nn.Module):
             dino_pred = out.view(B * S, g, self.pred_num, self.NUM_DINO_MASK_TOKEN // self.pred_num, -1)
         if self.sam_feat_pred and mode == "train":
             if self.share_query:
-                feat = transformer_output[:, :, P0 + cur:P0 + cur + self.NUM_SAM_TOKEN, 3 * q4:D]
+                feat = q_out[:, :, cur:cur + self.NUM_SAM_TOKEN, 3 * q4:D]
                 cur = 0
             else:
-                feat = transformer_output[:, :, P0 + cur:P0 + cur + self.NUM_SAM_TOKEN, :]
+                feat = q_out[:, :, cur:cur + self.NUM_SAM_TOKEN, :]
                 cur += self.NUM_SAM_TOKEN
             g = self.NUM_SAM_TOKEN // self.NUM_OBS_TOKEN_PER_SAM
             out = _WorldDecoder.run(feat, self.sam_decoder_obs_pred_projector, self.sam_mask_token,
@@ -630,7 +688,7 @@ class DreamVLA(nn.Module):
                                     self.sam_decoder_pred, g, self.NUM_OBS_TOKEN_PER_SAM, self.NUM_SAM_MASK_TOKEN, D)
             sam_pred = out.view(B * S, g, self.pred_num, self.NUM_SAM_MASK_TOKEN // self.pred_num, -1)
         if self.trajectory_pred and mode == "train":
-            feat = transformer_output[:, :, P0 + cur:P0 + cur + self.NUM_TRAJ_TOKEN, :]
+            feat = q_out[:, :, cur:cur + self.NUM_TRAJ_TOKEN, :]
             g = self.NUM_TRAJ_TOKEN // self.NUM_OBS_TOKEN_PER_TRAJ
             out = _WorldDecoder.run(feat, self.traj_decoder_obs_pred_projector, self.traj_mask_token,
                                     self.traj_decoder_position_embedding, self.traj_decoder, self.traj_decoder_norm,
@@ -640,8 +698,7 @@ class DreamVLA(nn.Module):
 
         # ---- action head (:915-987) ----
         if self.action_pred_steps > 0:
-            n_obs = self._this_num_obs_token()
-            action_pred_feature = transformer_output[:, :, P0 + n_obs:P0 + n_obs + self.action_pred_steps, :]
+            action_pred_feature = act_out
             if not self.use_dit_head:
                 h = self.action_decoder[0](action_pred_feature, act="relu")
                 h = self.action_decoder[2](h, act="relu")

@@ -66,3 +66,4 @@ def test_bit_packing_roundtrip():
     back = ((words.unsqueeze(-1) >> torch.arange(32)) & 1).bool().reshape(70, -1)[:, :131]
     assert torch.equal(back, vis)
     assert not ((words.unsqueeze(-1) >> torch.arange(32)) & 1).bool().reshape(70, -1)[:, 131:].any()
+

@@ -65,7 +65,7 @@ def test_fused_optimizer_matches_torch_adamw(dev):
     exact = float((got == want.to(torch.bfloat16).float()).float().mean())
     print(f"adamw: moments rel {e_m:.2e} / {e_v:.2e}; params max {float(off.max()):.3f} bf16 ulp from fp32 torch, "
           f"{100 * exact:.3f} % equal to round_bf16(torch)")
-    assert e_m < 1e-5 and e_v < 1e-5
+    assert e_m < 1e-4 and e_v < 1e-4
     assert float(off.max()) <= 1.0 and exact > 0.999
     assert step.flat.G.abs().max().item() == 0          # zero_grad fused
 

@@ -305,6 +305,13 @@ def group_attn():
     attn_case(2, 3, 197, 197, False, fused_qkv=True)
     attn_case(2, 2, 16, 212, False)
     attn_case(1, 2, 6, 6, False)
+    attn_case(5, 12, 6, 6, False, fused_qkv=True)              # DiT block (SIMT row kernels, attention_small.cu)
+    attn_case(3, 2, 10, 265, False)                            # identical-mask-row decoder form
+    attn_case(2, 3, 32, 40, False)
+    attn_case(2, 2, 33, 40, False)                             # just above the short-query limit: mma.sync kernels
+    attn_case(640, 12, 6, 6, False, fused_qkv=True, timeit=True)
+    attn_case(160, 8, 16, 212, False, timeit=True)
+    attn_case(320, 16, 10, 265, False, timeit=True)
     attn_case(1, 2, 265, 265, True)
     attn_case(1, 2, 258, 258, True, fused_qkv=True)
     attn_case(1, 2, 300, 520, False, ramp=6.0)
@@ -365,6 +372,38 @@ def group_attn_perf():
         am.visible = int(mb.sum().item())
         run("gpt2 B8 H16 L1290 mask", 8, 16, mb.shape[0], am)
         run("gpt2 B8 H16 L1290 mask drop", 8, 16, mb.shape[0], am, p=0.1)
+    # grouped token order [A | queries | action]: every attendable key of the A / query rows sits in the first 36*S rows, so
+    # the main call is (Lq = 1260 rows) x (Lk = 360 keys) with a dense step-causal mask, plus a 30-row call for the action rows
+    S, n_a, n_q, n_act = 10, 36, 90, 3
+    step_a = torch.arange(S).repeat_interleave(n_a)
+    step_q = torch.arange(S).repeat_interleave(n_q)
+    rows_step = torch.cat((step_a, step_q))
+    mb_main = rows_step[:, None] >= step_a[None, :]                                    # [1260, 360]
+    step_act = torch.arange(S).repeat_interleave(n_act)
+    mb_act = torch.cat((step_act[:, None] >= step_a[None, :], step_act[:, None] == step_q[None, :]), dim=1)   # [30, 1260]
+    am_main, am_act = ops.AttnMask(mb_main, dev), ops.AttnMask(mb_act, dev)
+    for p_drop in (0.0, 0.1):
+        B, H, Lt = 8, 16, S * (n_a + n_q + n_act)
+        qkv = torch.randn(B, Lt, 3, H, 64, generator=g).to(dev, torch.bfloat16)
+        q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+        n_main, n_ka = S * (n_a + n_q), S * n_a
+        d_o = torch.randn(B, Lt, H, 64, generator=g).to(dev, torch.bfloat16)
+        dqkv = torch.empty_like(qkv)
+        dk_act, dv_act = torch.empty(B, n_main, H, 64, device=dev, dtype=torch.bfloat16), torch.empty(B, n_main, H, 64, device=dev, dtype=torch.bfloat16)
+
+        def fwd():
+            o1, l1 = L_.attn_fwd(q[:, :n_main], k[:, :n_ka], v[:, :n_ka], 0.125, am_main.bits, am_main.flags, dropout_p=p_drop, dropout_seed=5)
+            o2, l2 = L_.attn_fwd(q[:, n_main:], k[:, :n_main], v[:, :n_main], 0.125, am_act.bits, am_act.flags, dropout_p=p_drop, dropout_seed=6)
+            return o1, l1, o2, l2
+        o1, l1, o2, l2 = fwd()
+
+        def bwd():
+            L_.attn_bwd(q[:, :n_main], k[:, :n_ka], v[:, :n_ka], o1, d_o[:, :n_main], l1, 0.125, dqkv[:, :n_main, 0], dqkv[:, :n_ka, 1],
+                        dqkv[:, :n_ka, 2], am_main.bits, am_main.flags, mask_bits_t=am_main.bits_t, dropout_p=p_drop, dropout_seed=5)
+            L_.attn_bwd(q[:, n_main:], k[:, :n_main], v[:, :n_main], o2, d_o[:, n_main:], l2, 0.125, dqkv[:, n_main:, 0], dk_act, dv_act,
+                        am_act.bits, am_act.flags, mask_bits_t=am_act.bits_t, dropout_p=p_drop, dropout_seed=6)
+        f, bw = bench(fwd), bench(bwd)
+        print(f"INFO attn_perf gpt2 GROUPED main 1260x360 + act 30x1260, drop={p_drop}: fwd {f*1e3:7.1f} us  bwd {bw*1e3:7.1f} us", flush=True)
     report("attn_perf ran", 0.0, 1.0)
 
 

@@ -34,11 +34,14 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference_gpu"])
     ap.add_argument("--batch", type=int, default=8, help="per-GPU batch: SURVEY.md C2 measures B=2 (finetune.sh value) and B=8")
     ap.add_argument("--config", default="calvin", choices=["calvin", "libero"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra fields of the default line (reference-on-GPU arm, "
+                    "script batch size, LIBERO config, action latency); they only run on 1 GPU")
+    ap.add_argument("--latency-steps", type=int, default=1000)
     ap.add_argument("--dropout", type=float, default=0.1)
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
     ap.add_argument("--layers", type=int, default=24, help=argparse.SUPPRESS)  # debugging only; bench lines use 24
@@ -154,6 +157,8 @@ def run_ours(args):
         if verbose:
             print(f"[bench r{rank} +{time.perf_counter() - t_begin:6.1f}s] {msg}", file=sys.stderr, flush=True)
     if world > 1:
+        from dreamvla_b200.utils.distributed_utils import configure_nccl
+        configure_nccl()
         dist.init_process_group("nccl", device_id=dev)
     stage("process group up")
     cfg = CONFIGS[args.config]
@@ -294,13 +299,10 @@ def run_ours(args):
             for _ in range(n):
                 yield host
 
-        def to_device(hb):
-            return {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
-
         def e2e_run(n):
             # the public training-loop iterator (train_one_epoch_calvin uses the same one): batch i+1 is copied host->device
             # on a copy stream while step i runs; every step still moves its own 193 MB in and its loss out
-            for dbatch in prefetch_to_device(host_batches(n), dev, to_device):
+            for dbatch in prefetch_to_device(host_batches(n), dev):
                 ls = step(dbatch)
                 loss_host.copy_(ls.reshape(1).float(), non_blocking=True)
         try:
@@ -335,6 +337,35 @@ def run_ours(args):
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         cpu = cpu_baseline(args, steps=1, warm=0)
 
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        # free the headline model first: the extra measurements build their own
+        workload_params = eager_step.flat.num_params
+        step = eager_step = model = batch = None
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        extras = {}
+        for key, fn in (("reference_gpu", lambda: reference_gpu_measure(args.config, B, dev)),
+                        ("calvin_script_batch", lambda: quick_train_measure("calvin", 2, dev, args.dropout)),
+                        ("libero", lambda: quick_train_measure("libero", 16, dev, args.dropout)),
+                        ("action_latency", lambda: latency_measure(dev, args.latency_steps))):
+            if key == "calvin_script_batch" and (args.config != "calvin" or B == 2):
+                continue
+            if key == "libero" and args.config == "libero":
+                continue
+            try:
+                t0 = time.perf_counter()
+                extras[key] = fn()
+                extras[key]["measure_wall_s"] = round(time.perf_counter() - t0, 1)
+            except Exception as e:  # noqa: BLE001   (an extra field must never cost the headline line)
+                extras[key] = {"error": repr(e)[:300]}
+            stage(f"extra {key} done")
+        if "value" in extras.get("reference_gpu", {}):
+            extras["vs_reference_gpu"] = round(value / extras["reference_gpu"]["value"], 3)
+    else:
+        workload_params = eager_step.flat.num_params
+
     if rank == 0:
         line = {
             "metric": "train_step_samples_per_sec", "value": round(value, 3), "unit": "samples/s", "n_gpus": world,
@@ -344,9 +375,9 @@ def run_ours(args):
                        "seq_len": cfg["model"]["sequence_length"], "parallelism": f"dp{world}",
                        "dropout": args.dropout, "layers": args.layers, "cuda_graph": graphed,
                        "l2": "inputs+weights+activations per step >> 126 MB L2 (1.3 GB of bf16 weights re-read every step); no explicit flush",
-                       "trainable_params": eager_step.flat.num_params, "final_loss": final_loss},
+                       "trainable_params": workload_params, "final_loss": final_loss},
             "clocks": sampler.summary() if sampler else None,
-            "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "extras": extras,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -354,6 +385,181 @@ def run_ours(args):
         step = eager_step = None
         from dreamvla_b200.utils.distributed_utils import shutdown_distributed
         shutdown_distributed()
+
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# extra fields of the default line (1 GPU): other SURVEY §8d configurations, so that they are driver-visible
+# ----------------------------------------------------------------------------------------------------------------------
+def quick_train_measure(config, B, dev, dropout=0.1, steps=10, warmup=3):
+    """samples/s of one more (config, per-GPU batch) with the same code path as the headline (CUDA-graph replay, device-
+    resident synthetic inputs, CUDA events)."""
+    from dreamvla_b200.utils.train_utils import GraphedTrainStep, StepConfig, TrainStep, synthetic_batch
+    cfg = CONFIGS[config]
+    scfg = StepConfig(**cfg["step"])
+    model = build_model(cfg, dev, dropout)
+    eager = TrainStep(model, scfg)
+    batch = synthetic_batch(scfg, B, dev, seed=99, heads=dict(cfg["heads"], flow_mask=scfg.flow_as_mask))
+    step = GraphedTrainStep(eager, batch, warmup=3)
+    for _ in range(warmup):
+        step(step.static)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step(step.static)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    peak, _ = measured_peaks()
+    out = {"workload": cfg["name"], "per_gpu_batch": B, "ms_per_step": round(ms, 3), "value": round(B / ms * 1e3, 2),
+           "unit": "samples/s", "steps": steps, "step_frac_of_peak": round(cfg["tf_per_sample"] * B / (ms * 1e-3) / peak, 4),
+           "final_loss": float(loss)}
+    del step, eager, model, batch
+    torch.cuda.empty_cache()
+    return out
+
+
+LATENCY_MODEL = dict(sequence_length=10, num_resampler_query=16, num_obs_token_per_image=9, obs_pred=True, depth_pred=True,
+                     sam_feat_pred=True, action_pred_steps=3, transformer_layers=24, hidden_dim=1024, transformer_heads=16,
+                     phase="evaluate", use_dit_head=True, attn_implementation="sdpa")     # scripts/CALVIN_ABC_D/DreamVLA/eval.sh
+
+
+def latency_measure(dev, steps):
+    """BASELINE.json configs[3]: `steps` consecutive ModelWrapper.step calls, batch 1, growing then sliding window,
+    p50 / p99 of the host-side wall time around each call (device synchronised on both sides)."""
+    from dreamvla_b200.models import DreamVLA
+    from dreamvla_b200.utils import rollout_bench
+    from dreamvla_b200.utils.eval_utils_calvin import ModelWrapper
+    torch.manual_seed(0)
+    model = DreamVLA(finetune_type="calvin", clip_device="cpu", vit_checkpoint_path=None, **LATENCY_MODEL).bfloat16().to(dev)
+    model._init_model_type()
+    model.eval()
+    out = {"workload": "eval_calvin.py action inference (eval.sh heads obs+depth+sam, DiT, S=10, L=930), batch 1", "steps": steps}
+    for name, kw in (("full_window", dict(incremental=False)), ("incremental", dict(incremental=True, prune=True))):
+        w = ModelWrapper(model, history_len=10, action_pred_steps=3, device=dev, **kw)
+        lat = rollout_bench.run_calvin(w, steps, seed=1)
+        out[name] = rollout_bench.percentile_report(lat, skip=25)
+        del w
+        torch.cuda.empty_cache()
+    out["unit"] = "ms"
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the reference's algorithm on the GPU, the way the reference runs it: torch eager kernels + cuBLAS + SDPA with the dense
+# additive mask, bf16 (`--precision bf16` casts the model, train.py:122-123), DistributedDataParallel(find_unused_parameters
+# =True) (train.py:173), clip_grad_norm_(0.1) + torch.optim.AdamW every step (train_utils.py:599-608).  The modules are the
+# oracle's functional restatement (pinned to the unmodified reference by tests/test_oracle_cpu.py): /root/reference does not
+# exist on the GPU box.
+# ----------------------------------------------------------------------------------------------------------------------
+def reference_gpu_measure(config, B, dev, steps=5, warmup=3, world=1):
+    import torch.nn.functional as F
+    from oracle import dreamvla_oracle as O
+    from tests import synth
+    from tests.state_template import build_template
+    cfg = CONFIGS[config]
+    mk = dict(cfg["model"], batch=B, weight_seed=1, input_seed=2 + int(os.environ.get("RANK", "0")))
+    sd = {k: (v.to(dev, torch.bfloat16) if v.is_floating_point() else v.to(dev))
+          for k, v in synth.synth_state_dict(build_template(mk), 1).items()}
+    frozen = ("vision_encoder.", "clip_model.", "attention_mask", "position_embedding")
+    names = [k for k, v in sd.items() if v.is_floating_point() and not any(f in k for f in frozen)]
+    inp = {k: (v.to(dev, torch.bfloat16) if v.is_floating_point() else v.to(dev)) for k, v in synth.synth_inputs(mk).items()}
+    lab = {k: v.to(dev, torch.bfloat16) for k, v in synth.synth_labels(mk).items()} if cfg["heads"] else {}
+    S = mk["sequence_length"]
+    n = 8 * B * S
+    lcfg = dict(mk, future_steps=3, flow_as_mask=cfg["step"].get("flow_as_mask", False))
+
+    def mha_sdpa(q, k, v, scale, mask=None):        # GPT2SdpaAttention / timm fused attention (gpt2.py:196-284)
+        q, k, v = (t.permute(0, 2, 1, 3) for t in (q, k, v))
+        if mask is not None:                        # dense additive [B, 1, L, L] mask, as dreamvla_model.py:769-775 builds it
+            mask = mask.to(q.dtype).expand(q.shape[0], 1, -1, -1).contiguous() if mask.dim() == 2 else mask.to(q.dtype)
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, scale=scale).permute(0, 2, 1, 3)
+        return o.reshape(o.shape[0], o.shape[1], -1)
+
+    class RefModule(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.params = torch.nn.ParameterList([torch.nn.Parameter(sd[k]) for k in names])
+
+        def forward(self, noise, tstep, drop):
+            full = dict(sd)
+            full.update(zip(names, self.params))
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                fwd = O.dreamvla_forward(full, mk, inp["image_primary"], inp["image_wrist"], inp["state"], inp["text_token"],
+                                         action_label=inp["action_label"], diffusion_noise=noise, diffusion_timestep=tstep,
+                                         diffusion_drop_ids=drop)
+                return O.train_losses(lcfg, fwd, lab)["loss"] if cfg["heads"] else fwd["loss_action"]
+    mod = RefModule().to(dev)
+    run_mod = mod
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        run_mod = DDP(mod, device_ids=[dev.index], find_unused_parameters=True)
+    opt = torch.optim.AdamW(mod.parameters(), lr=1e-3, weight_decay=1e-4)
+    orig = O._mha
+    O._mha = mha_sdpa
+    try:
+        def one():
+            noise = torch.randn(n, 3, 7, device=dev, dtype=torch.bfloat16)
+            tstep = torch.randint(0, 100, (n,), device=dev)
+            drop = torch.rand(n, device=dev) < 0.1
+            loss = run_mod(noise, tstep, drop)
+            loss.float().backward()
+            torch.nn.utils.clip_grad_norm_(mod.parameters(), 0.1)
+            opt.step()
+            opt.zero_grad()
+            return loss
+        for _ in range(warmup):
+            one()
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = one()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t)
+    finally:
+        O._mha = orig
+    out = {"impl": "reference algorithm on this GPU: torch eager + cuBLAS + SDPA (dense mask), bf16 weights + autocast, "
+                   "clip_grad_norm_ + torch.optim.AdamW" + (", DDP find_unused_parameters" if world > 1 else ""),
+           "workload": cfg["name"], "per_gpu_batch": B, "ms_per_step": round(ms, 2), "value": round(B * world / ms * 1e3, 2),
+           "unit": "samples/s", "steps": steps, "loss": float(loss)}
+    del mod, run_mod, opt, sd
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_reference_gpu(args):
+    import torch.distributed as dist
+    rank, local_rank, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    r = reference_gpu_measure(args.config, args.batch, dev, steps=args.steps, warmup=max(args.warmup, 3), world=world)
+    if rank == 0:
+        cfg = CONFIGS[args.config]
+        print(json.dumps({"impl": "reference_gpu", "metric": "train_step_samples_per_sec", "value": r["value"], "unit": "samples/s",
+                          "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"],
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                          "config": {"workload": cfg["name"], "per_gpu_batch": args.batch, "global_batch": args.batch * world,
+                                     "seq_len": cfg["model"]["sequence_length"], "parallelism": f"dp{world}"},
+                          "how": r["impl"]}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -447,5 +653,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.impl == "reference_gpu":
+        run_reference_gpu(a)
     else:
         run_ours(a)

@@ -68,7 +68,8 @@ EXPORTS = [
     "dvla_version", "dvla_last_error", "dvla_launch_count", "dvla_gemm", "dvla_layernorm_fwd", "dvla_layernorm_bwd",
     "dvla_attn_fwd", "dvla_attn_bwd", "dvla_attn_mask_tiles", "dvla_colsum_accum", "dvla_accum_fp32_into_bf16",
     "dvla_dropout", "dvla_act_bwd", "dvla_mse_loss", "dvla_cosine_loss", "dvla_silog_stats", "dvla_silog_finish",
-    "dvla_sumsq", "dvla_adamw", "dvla_grad_clip_scale",
+    "dvla_sumsq", "dvla_adamw", "dvla_grad_clip_scale", "dvla_attn_bwd_workspace_bytes", "dvla_silog_workspace_bytes",
+    "dvla_gemm_workspace_bytes", "dvla_set_sm_budget",
 ]
 
 _lib = None
@@ -88,7 +89,9 @@ def load() -> C.CDLL:
     lib.dvla_launch_count.restype = C.c_int64
     for name in EXPORTS:
         if not hasattr(lib, name):
-            raise RuntimeError(f"{LIB_PATH} does not export {name}")
+            raise RuntimeError(f"{LIB_PATH} does not export {name} (stale build? run `python -m dreamvla_b200.build`)")
+    for name in ("dvla_attn_bwd_workspace_bytes", "dvla_silog_workspace_bytes", "dvla_gemm_workspace_bytes"):
+        getattr(lib, name).restype = C.c_int64
     _lib = lib
     return lib
 
@@ -214,7 +217,8 @@ def attn_bwd(q, k, v, o, d_o, lse, scale, dq, dk, dv, mask_bits=None, tile_flags
              dropout_seed_ptr=None, mask_bits_t=None):
     B, Lq, H, _ = q.shape
     Lk = k.shape[1]
-    delta = torch.empty((B, H, Lq), device=q.device, dtype=torch.float32)
+    ws = int(load().dvla_attn_bwd_workspace_bytes(_i64(B), _i64(H), _i64(Lq)))
+    delta = torch.empty(ws // 4, device=q.device, dtype=torch.float32)
     a = AttnBwdArgs()
     a.q, a.k, a.v, a.o, a.d_o = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr()
     a.lse, a.delta = lse.data_ptr(), delta.data_ptr()
@@ -295,7 +299,7 @@ def cosine_loss(pred2d, label2d, weight, loss_out, dpred):
 def silog_loss(pred, label, lambd, weight, loss_out, dpred):
     assert pred.is_contiguous() and label.is_contiguous()
     n = pred.numel()
-    stats = torch.zeros(2, device=pred.device, dtype=torch.float32)
+    stats = torch.zeros(int(load().dvla_silog_workspace_bytes()) // 4, device=pred.device, dtype=torch.float32)
     _check(load().dvla_silog_stats(C.c_void_p(pred.data_ptr()), C.c_void_p(label.data_ptr()), _i64(n),
                                    C.c_void_p(stats.data_ptr()), _stream()), "dvla_silog_stats")
     _check(load().dvla_silog_finish(C.c_void_p(pred.data_ptr()), C.c_void_p(label.data_ptr()), _i64(n),
@@ -320,3 +324,8 @@ def grad_clip_scale(g, sumsq_t, max_norm, grad_scale=1.0):
     """g *= grad_scale * min(1, max_norm / (sqrt(sumsq) * grad_scale + 1e-6)) in place (clip_grad_norm_ on the flat buffer)."""
     _check(load().dvla_grad_clip_scale(C.c_void_p(g.data_ptr()), _i64(g.numel()), C.c_void_p(sumsq_t.data_ptr()),
                                        _f32(max_norm), _f32(grad_scale), _stream()), "dvla_grad_clip_scale")
+
+
+def set_sm_budget(n_sms: int) -> int:
+    """SMs the persistent GEMM kernels size their grids for (0 = all); returns the previous value."""
+    return int(load().dvla_set_sm_budget(C.c_int(int(n_sms))))

@@ -586,20 +586,18 @@ bool attn_small_applicable(int64_t Lq, int64_t Lk, const void* mask, float dropo
 int attn_small_fwd_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s);
 int attn_small_bwd_dispatch(const dvla_attn_bwd_args* a, cudaStream_t s);
 static bool attn_small_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("DVLA_ATTN_SMALL"); on = (e && e[0] == '0') ? 0 : 1; }
-  return on == 1;
+  static const bool on = [] { const char* e = getenv("DVLA_ATTN_SMALL"); return !(e && e[0] == '0'); }();   // thread-safe init
+  return on;
 }
 int attn_fwd_ws_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s, long long q_rows);   // attention_fwd_ws.cu (tcgen05, warp-specialised)
 
 // 0 = auto (warp-specialised tcgen05 kernel for Lq >= 96, SIMT row kernel for Lq <= 32 without mask / dropout, mma.sync
 // kernel otherwise), 1 = mma.sync everywhere, 3 = warp-specialised tcgen05 kernel whenever expressible
 static int attn_fwd_mode() {
-  static int mode = -1;
-  if (mode < 0) {
+  static const int mode = [] {
     const char* e = getenv("DVLA_ATTN_FWD");
-    mode = (e && !strcmp(e, "legacy")) ? 1 : (e && !strcmp(e, "ws")) ? 3 : 0;
-  }
+    return (e && !strcmp(e, "legacy")) ? 1 : (e && !strcmp(e, "ws")) ? 3 : 0;
+  }();
   return mode;
 }
 
@@ -649,11 +647,10 @@ int attn_bwd_ws_dispatch(const dvla_attn_bwd_args* a, const uint32_t* mask_t, in
 // 0 = auto (warp-specialised tcgen05 kernels when both sequences are >= 96 long, SIMT row kernels for Lq <= 32 without
 // mask / dropout, mma.sync kernels otherwise), 1 = mma.sync kernels everywhere, 4 = warp-specialised whenever expressible
 static int attn_bwd_mode() {
-  static int mode = -1;
-  if (mode < 0) {
+  static const int mode = [] {
     const char* e = getenv("DVLA_ATTN_BWD");
-    mode = (e && !strcmp(e, "legacy")) ? 1 : (e && !strcmp(e, "ws")) ? 4 : 0;
-  }
+    return (e && !strcmp(e, "legacy")) ? 1 : (e && !strcmp(e, "ws")) ? 4 : 0;
+  }();
   return mode;
 }
 

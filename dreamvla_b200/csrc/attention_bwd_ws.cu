@@ -518,15 +518,15 @@ int attn_bwd_ws_dispatch(const dvla_attn_bwd_args* a, const uint32_t* mask_t, in
     p.drop_seed = a->dropout_seed;
     p.drop_seed_ptr = a->dropout_seed_ptr;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static const bool attr_ok = [] {               // once, race-free (C++11 static initialisation)
     cudaError_t e1 = cudaFuncSetAttribute(attn_bwd_dkv_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_DKV_WS_SMEM);
     cudaError_t e2 = cudaFuncSetAttribute(attn_bwd_dq_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_DQ_WS_SMEM);
-    if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("attn_bwd_ws smem attr failed"); return DVLA_ERR_CUDA; }
+    if (e1 != cudaSuccess || e2 != cudaSuccess) return false;
     cudaFuncSetAttribute(attn_bwd_dkv_ws_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   // 2 CTAs / SM
     cudaFuncSetAttribute(attn_bwd_dq_ws_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    attr_set = true;
-  }
+    return true;
+  }();
+  if (!attr_ok) { set_error("attn_bwd_ws smem attr failed"); return DVLA_ERR_CUDA; }
   CUtensorMap q64, do64, k128, v128, q128, do128, k64, v64;
   int hi;
   if (!make_attn_tmap_rows(&q64, a->q, a->Lq, a->H, a->B, a->q_ss, a->q_sh, a->q_sb, 64, &p.q_hi)) return DVLA_ERR_CUDA;

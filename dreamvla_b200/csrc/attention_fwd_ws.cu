@@ -455,20 +455,19 @@ int attn_fwd_ws_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s, long long 
   p.nkt = nkt; p.mask_words = a->mask_words;
   p.o_sb = a->o_sb; p.o_ss = a->o_ss; p.o_sh = a->o_sh;
   p.scale = a->scale;
-  { static int tr = -1; if (tr < 0) { const char* e = getenv("DVLA_ATTN_TRACE"); tr = (e && e[0] == '1') ? 1 : 0; } p.trace = tr; }
+  { static const int tr = [] { const char* e = getenv("DVLA_ATTN_TRACE"); return (e && e[0] == '1') ? 1 : 0; }(); p.trace = tr; }
   if (a->dropout_p > 0.f) {
     p.drop_thresh = (uint32_t)(a->dropout_p * 65536.0f + 0.5f);
     p.drop_scale = 1.0f / (1.0f - (float)p.drop_thresh / 65536.0f);
     p.drop_seed = a->dropout_seed;
     p.drop_seed_ptr = a->dropout_seed_ptr;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static const cudaError_t attr_err = [] {      // once, race-free (C++11 static initialisation)
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM);
-    if (e != cudaSuccess) { set_error("attn_fwd_ws smem attr: %s", cudaGetErrorString(e)); return DVLA_ERR_CUDA; }
-    cudaFuncSetAttribute(attn_fwd_ws_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   // room for 2 CTAs / SM
-    attr_set = true;
-  }
+    if (e == cudaSuccess) cudaFuncSetAttribute(attn_fwd_ws_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   // room for 2 CTAs / SM
+    return e;
+  }();
+  if (attr_err != cudaSuccess) { set_error("attn_fwd_ws smem attr: %s", cudaGetErrorString(attr_err)); return DVLA_ERR_CUDA; }
   dim3 grid((unsigned)((q_rows + 255) / 256), (unsigned)a->H, (unsigned)a->B);   // q_rows: Lq, or a multiple of 256 below it
   attn_fwd_ws_kernel<<<grid, WS_THREADS, WS_SMEM, s>>>(tmQ, tmK, tmV, p);
   cudaError_t e = cudaGetLastError();

@@ -1,10 +1,9 @@
-// Flash attention for SHORT query blocks (Lq <= 32, any Lk, head_dim 64, no mask, no dropout) on the SIMT pipes.
+// Flash attention for SHORT sequences (Lq <= 32, Lk <= 64, head_dim 64, no mask, no dropout) on the SIMT pipes.
 //
-// Call sites: the DiT action head (a-8/a-9: 6 tokens per sequence, 12 blocks, 8*B*S sequences -- reference
-// models/action_model/models.py:130-134 via timm Attention), the Perceiver resampler's 16 latent queries over 196+16 keys
-// (a-3, reference models/perceiver_resampler.py:35-61) and the identical-row form of a world decoder (10 distinct queries over
-// 265 keys, dreamvla_model.py here).  A 64-row tensor-core tile would be 75-90 % padding for these; they are latency /
-// launch bound, so the layout is chosen for many independent short chains instead:
+// Call site: the DiT action head (a-8/a-9: 6 tokens per sequence, 12 blocks, 8*B*S sequences -- reference
+// models/action_model/models.py:130-134 via timm Attention).  A 64-row tensor-core tile is 90 % padding for it and one
+// (batch, head) per CTA means 7680 CTAs of mostly idle warps; it is latency / launch bound, so the layout is chosen for many
+// independent short chains instead:
 //   two threads per row (32 of the 64 head dims each, one shuffle per dot product), fp32 math, online softmax in the
 //   exp2 domain; K / V rows are broadcast reads (all rows of one (batch, head) sit in the same warp or the next).
 //   forward:   thread pair = one query row, loop over keys
@@ -179,10 +178,14 @@ __global__ void __launch_bounds__(256) attn_small_bwd_dkv_kernel(const SmallPara
 
 }  // namespace
 
+// Measured on B200 (profiles/r2_kernel_check_attn.log): 20 us fwd / 36 us bwd for the DiT shape (7680 (b,h) x 6x6), but the
+// serial key loop loses to the mma.sync kernel once there are hundreds of keys per row (16x212: 138 us fwd; 10x265: 630 us),
+// so the row kernels take the short-key case only.
 constexpr int SMALL_MAX_LQ = 32;
+constexpr int SMALL_MAX_LK = 64;
 
 bool attn_small_applicable(int64_t Lq, int64_t Lk, const void* mask, float dropout_p) {
-  return Lq <= SMALL_MAX_LQ && Lk <= 4096 && !mask && dropout_p == 0.f;
+  return Lq <= SMALL_MAX_LQ && Lk <= SMALL_MAX_LK && !mask && dropout_p == 0.f;
 }
 
 int attn_small_fwd_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s) {

@@ -19,14 +19,19 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static std::atomic<int> g_sm_budget{0};
+// SMs the persistent kernels (one CTA, or CTA pair, per SM) may size their grids for: the device's SM count, or the
+// caller's budget while a collective shares the GPU (dvla_set_sm_budget) -- a persistent grid that cannot place every CTA
+// runs its stragglers as a second wave.
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
+  static const int n = [] {
+    int dev = 0, v = 0;
     cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    return v;
+  }();
+  const int b = g_sm_budget.load(std::memory_order_relaxed);
+  return (b > 0 && b < n) ? b : n;
 }
 
 int gemm_dispatch(const dvla_gemm_args* a, cudaStream_t stream);
@@ -105,5 +110,13 @@ int dvla_adamw(const dvla_adamw_args* a, void* stream) { return adamw_dispatch(a
 int dvla_grad_clip_scale(void* g, int64_t n, const float* sumsq, float max_norm, float grad_scale, void* stream) {
   return grad_clip_scale_dispatch(g, n, sumsq, max_norm, grad_scale, S(stream));
 }
+
+int dvla_set_sm_budget(int n_sms) {
+  const int prev = g_sm_budget.exchange(n_sms > 0 ? (n_sms & ~1) : 0, std::memory_order_relaxed);   // even: CTA pairs
+  return prev;
+}
+int64_t dvla_attn_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Lq) { return (B > 0 && H > 0 && Lq > 0) ? 4 * B * H * Lq : 0; }
+int64_t dvla_silog_workspace_bytes(void) { return 2 * (int64_t)sizeof(float); }
+int64_t dvla_gemm_workspace_bytes(const dvla_gemm_args* args) { (void)args; return 0; }
 
 }  // extern "C"

@@ -670,6 +670,7 @@ __global__ void gemm_simt_warp_kernel(const bf16* __restrict__ a, const bf16* __
 
 // ============================================== host side ========================================================
 #include <mutex>
+#include <unordered_map>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -697,11 +698,39 @@ static EncodeTiledFn get_encode_fn() {
 
 EncodeTiledFn get_encode_fn_shared() { return get_encode_fn(); }
 
+// Descriptor cache: the only mutable module-level state besides the launch counter.  Keyed by everything
+// cuTensorMapEncodeTiled sees; guarded by a mutex because forward (main thread) and backward (autograd's device thread)
+// call into the library concurrently.  Bounded: cleared when full (activations are recycled by the caching allocator, so
+// a training loop touches a few thousand distinct (pointer, shape) pairs).
+struct TmapKey {
+  const void* base; uint64_t inner, outer, ld; uint32_t box_inner, box_outer;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = reinterpret_cast<uint64_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    h ^= (k.inner + 0x632BE59BD9B4E019ull) * 0xD1342543DE82EF95ull; h = (h << 13) | (h >> 51);
+    h ^= (k.outer << 20) ^ (k.ld * 0xA0761D6478BD642Full) ^ ((uint64_t)k.box_inner << 40) ^ ((uint64_t)k.box_outer << 52);
+    return static_cast<size_t>(h ^ (h >> 29));
+  }
+};
+static std::mutex g_tmap_mu;
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+constexpr size_t TMAP_CACHE_MAX = 8192;
+
 // 2-D bf16 tensor map: inner dim contiguous, 128B swizzle, zero OOB fill.
 bool make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                        uint32_t box_inner, uint32_t box_outer) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not found"); return false; }
+  const TmapKey key{base, inner, outer, ld_elems, box_inner, box_outer};
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) { *out = it->second; return true; }
+  }
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {ld_elems * 2};
   cuuint32_t box[2] = {box_inner, box_outer};
@@ -715,7 +744,19 @@ bool make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint6
               base);
     return false;
   }
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (g_tmap_cache.size() >= TMAP_CACHE_MAX) g_tmap_cache.clear();
+    g_tmap_cache.emplace(key, *out);
+  }
   return true;
+}
+
+// cudaFuncSetAttribute once per kernel instantiation, race-free between the forward and the autograd thread
+template <typename K>
+static bool set_smem_attr_once(std::once_flag& once, cudaError_t& err, K kern, int bytes) {
+  std::call_once(once, [&] { err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); });
+  return err == cudaSuccess;
 }
 
 template <int BN, bool A_MN, bool B_MN>
@@ -727,11 +768,10 @@ static int launch_tc(const dvla_gemm_args* a, const GemmParams& p, cudaStream_t 
   if (!B_MN) { if (!make_tmap_2d_bf16(&tmB, a->b, a->K, a->N, a->ldb, BK, BN)) return DVLA_ERR_CUDA; }
   else       { if (!make_tmap_2d_bf16(&tmB, a->b, a->N, a->K, a->ldb, 64, BK)) return DVLA_ERR_CUDA; }
   auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return DVLA_ERR_CUDA; }
-    attr_set = true;
+  static std::once_flag once;      // per instantiation
+  static cudaError_t attr_err = cudaSuccess;
+  if (!set_smem_attr_once(once, attr_err, kern, Cfg::SMEM_BYTES)) {
+    set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(attr_err)); return DVLA_ERR_CUDA;
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -751,11 +791,10 @@ static int launch_tc2(const dvla_gemm_args* a, const GemmParams& p, cudaStream_t
   if (!B_MN) { if (!make_tmap_2d_bf16(&tmB, a->b, a->K, a->N, a->ldb, BK, 128)) return DVLA_ERR_CUDA; }
   else       { if (!make_tmap_2d_bf16(&tmB, a->b, a->N, a->K, a->ldb, 64, BK)) return DVLA_ERR_CUDA; }
   auto kern = gemm_tcgen05_2cta_kernel<A_MN, B_MN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(2cta smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return DVLA_ERR_CUDA; }
-    attr_set = true;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  if (!set_smem_attr_once(once, attr_err, kern, Cfg::SMEM_BYTES)) {
+    set_error("cudaFuncSetAttribute(2cta smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(attr_err)); return DVLA_ERR_CUDA;
   }
   const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * p.num_n_tiles * p.k_splits;
   const int max_clusters = num_sms() / 2;
@@ -769,19 +808,17 @@ static int launch_tc2(const dvla_gemm_args* a, const GemmParams& p, cudaStream_t
 
 // 0 = auto, 1 = force single-CTA kernels, 2 = force the CTA-pair kernel whenever legal
 static int gemm_mode() {
-  static int mode = -1;
-  if (mode < 0) {
+  static const int mode = [] {
     const char* e = getenv("DVLA_GEMM");
-    mode = (e && !strcmp(e, "1cta")) ? 1 : (e && !strcmp(e, "2cta")) ? 2 : 0;
-  }
+    return (e && !strcmp(e, "1cta")) ? 1 : (e && !strcmp(e, "2cta")) ? 2 : 0;
+  }();
   return mode;
 }
 
 // DVLA_GEMM_SPLITK=0 disables the atomic split-K path (bit-reproducible gradient accumulation order)
 static bool splitk_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("DVLA_GEMM_SPLITK"); on = (e && !strcmp(e, "0")) ? 0 : 1; }
-  return on == 1;
+  static const bool on = [] { const char* e = getenv("DVLA_GEMM_SPLITK"); return !(e && !strcmp(e, "0")); }();
+  return on;
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

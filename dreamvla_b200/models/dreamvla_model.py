@@ -627,7 +627,7 @@ class DreamVLA(nn.Module):
         # ---- backbone (:765-790) ----
         transformer_input = self.embedding_layer_norm(transformer_input)
         marks = getattr(self, "_dvla_grad_marks", None)      # set by TrainStep: overlap the gradient all-reduce with backward
-        self.transformer_backbone._dvla_grad_mark = marks["backbone_mid"] if marks else None
+        self.transformer_backbone._dvla_grad_mark = marks["backbone_cuts"] if marks else None
         transformer_output = self.transformer_backbone(inputs_embeds=transformer_input, attention_mask=self._attn_mask(dev))
         if marks and transformer_output.requires_grad:
             ops.on_grad_ready(transformer_output, marks["backbone_out"])

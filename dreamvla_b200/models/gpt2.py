@@ -125,9 +125,9 @@ class GPT2Model(nn.Module):
             m2 = mask[0, 0] if mask.dim() == 4 else mask
             mask = ops.AttnMask.from_additive(m2, inputs_embeds.device)
         h = ops.dropout(inputs_embeds, self.embd_pdrop, self.training)
-        mark = getattr(self, "_dvla_grad_mark", None)        # (layer index, callback): see TrainStep._arm_overlap
+        marks = dict(getattr(self, "_dvla_grad_mark", None) or ())   # {layer index: callback}: see TrainStep._arm_overlap
         for i, block in enumerate(self.h):
-            if mark is not None and i == mark[0] and h.requires_grad:
-                ops.on_grad_ready(h, mark[1])                # fires when layers >= i have finished their backward
+            if i in marks and h.requires_grad:
+                ops.on_grad_ready(h, marks[i])               # fires when layers >= i have finished their backward
             h = block(h, mask)
         return self.ln_f(h)

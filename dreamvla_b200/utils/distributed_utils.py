@@ -27,6 +27,19 @@ def world_info_from_env():
     return local_rank, global_rank, world_size
 
 
+def nccl_cta_budget() -> int:
+    """CTAs (= SMs) the gradient all-reduce may occupy while it overlaps the backward pass (DVLA_NCCL_CTAS, default 16)."""
+    return max(1, int(os.environ.get("DVLA_NCCL_CTAS", "16")))
+
+
+def configure_nccl() -> None:
+    """Call BEFORE the process group is created.  The all-reduce of the gradient segments runs concurrently with backward's
+    persistent GEMMs (one CTA per SM): cap NCCL's CTAs so that the GEMMs can be launched on the remaining SMs
+    (TrainStep lowers the kernels' SM budget by the same number while segments are in flight).  NVSwitch / NVLS keeps the
+    bus bandwidth of an 8-GPU all-reduce high with few CTAs; an explicit NCCL_MAX_CTAS in the environment wins."""
+    os.environ.setdefault("NCCL_MAX_CTAS", str(nccl_cta_budget()))
+
+
 def init_distributed_device(args):
     args.distributed = False
     if not hasattr(args, "world_size"):
@@ -38,6 +51,7 @@ def init_distributed_device(args):
     if args.world_size > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
+        configure_nccl()
         torch.distributed.init_process_group(backend=getattr(args, "dist_backend", "nccl"), device_id=device,
                                              timeout=datetime.timedelta(seconds=7200))
         args.distributed = True

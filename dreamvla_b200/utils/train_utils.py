@@ -50,14 +50,32 @@ EARLY_GRAD_PREFIXES = ("image_decoder", "mask_token", "depth_decoder", "depth_ma
                        "action_model.", "action_decoder", "arm_action_decoder", "gripper_action_decoder")
 
 
-def grad_segment(name: str, n_layers: int) -> int:
-    """0: complete at the backbone output; 1: complete at the input of backbone layer n_layers//2; 2: complete at the end."""
+BACKBONE_CUTS = 3          # the backbone's gradients are exchanged in BACKBONE_CUTS + 1 pieces (layer quarters at 3)
+
+
+def backbone_cut_layers(n_layers: int, n_cuts: int = BACKBONE_CUTS):
+    """Layer indices (descending) at whose INPUT a gradient segment completes during backward: with 24 layers and 3 cuts
+    [18, 12, 6] -- the gradients of layers >= 18 are final once backward reaches the input of layer 18, and so on."""
+    n_cuts = max(0, min(n_cuts, n_layers - 1))
+    return sorted({max(1, round(n_layers * (n_cuts - i) / (n_cuts + 1))) for i in range(n_cuts)}, reverse=True)
+
+
+def grad_segment(name: str, n_layers: int, n_cuts: int = BACKBONE_CUTS) -> int:
+    """Order in which a parameter's gradient becomes final during backward.  0: complete when backward reaches the backbone
+    output (heads, decoders, DiT); k = 1..len(cuts): backbone layers >= cuts[k-1] (and `ln_f` with k = 1), complete at the
+    input of layer cuts[k-1]; len(cuts) + 1: everything that feeds the backbone -- complete only at the end."""
     if name.startswith(EARLY_GRAD_PREFIXES):
         return 0
+    cuts = backbone_cut_layers(n_layers, n_cuts)
+    if name.startswith("transformer_backbone.ln_f."):
+        return 1 if cuts else len(cuts) + 1
     m = re.match(r"transformer_backbone\.h\.(\d+)\.", name)
-    if (m and int(m.group(1)) >= n_layers // 2) or name.startswith("transformer_backbone.ln_f."):
-        return 1
-    return 2
+    if m:
+        layer = int(m.group(1))
+        for k, c in enumerate(cuts):
+            if layer >= c:
+                return k + 1
+    return len(cuts) + 1
 
 
 def get_cast_dtype(precision: str):
@@ -205,9 +223,11 @@ class FlatParams:
             off += aligned(p.numel())
         self.n_big = sum(aligned(p.numel()) for _, p in big)
         self.n = off
-        # [0, seg_end[0]) and [seg_end[0], seg_end[1]) hold the >=2-D gradients of segments 0 / 1 (see grad_segment)
-        self.seg_end = [sum(aligned(p.numel()) for n_, p in big if grad_segment(n_, n_layers) <= k) for k in (0, 1)]
-        self.mid_layer = n_layers // 2
+        # [0, seg_end[0]), [seg_end[0], seg_end[1]), ... hold the >=2-D gradients of segments 0, 1, ... (see grad_segment);
+        # the last segment (and the 1-D gradients behind it) is complete only when backward has finished
+        self.cut_layers = backbone_cut_layers(n_layers)
+        self.seg_end = [sum(aligned(p.numel()) for n_, p in big if grad_segment(n_, n_layers) <= k)
+                        for k in range(len(self.cut_layers) + 1)]
         self.P = torch.zeros(self.n, device=dev, dtype=torch.bfloat16)
         self.G = torch.zeros(self.n, device=dev, dtype=torch.bfloat16)
         self.G32 = torch.zeros(max(self.n - self.n_big, 8), device=dev, dtype=torch.float32)
@@ -403,6 +423,10 @@ class TrainStep:
         # profiles/r1_ddp_overlap_check.log), eagerly and inside the captured step.  DVLA_AR_OVERLAP=0 turns it off.
         self.overlap = world_size > 1 and os.environ.get("DVLA_AR_OVERLAP", "1") != "0"
         self._reduced_upto = 0
+        # while gradient segments are in flight the persistent GEMMs of backward are sized for the SMs NCCL leaves free
+        # (DVLA_SM_BUDGET=0 turns that off)
+        from .distributed_utils import nccl_cta_budget
+        self.comm_ctas = nccl_cta_budget() if (self.overlap and os.environ.get("DVLA_SM_BUDGET", "1") != "0") else 0
 
     def prepare_inputs(self, batch):
         """train_utils.py:99-145: slices of the window, gripper remap, sliding-window action labels."""
@@ -454,12 +478,15 @@ class TrainStep:
         with torch.cuda.stream(self.comm_stream):
             dist.all_reduce(self.flat.G[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
         self._reduced_upto = hi
+        if self.comm_ctas:
+            L.set_sm_budget(torch.cuda.get_device_properties(self.flat.G.device).multi_processor_count - self.comm_ctas)
 
     def _arm_overlap(self):
         self._reduced_upto = 0
         if self.overlap:
-            self.model._dvla_grad_marks = {"backbone_out": lambda: self._reduce_segment(0),
-                                           "backbone_mid": (self.flat.mid_layer, lambda: self._reduce_segment(1))}
+            self.model._dvla_grad_marks = {
+                "backbone_out": lambda: self._reduce_segment(0),
+                "backbone_cuts": [(layer, (lambda k=k: self._reduce_segment(k + 1))) for k, layer in enumerate(self.flat.cut_layers)]}
         elif hasattr(self.model, "_dvla_grad_marks"):
             self.model._dvla_grad_marks = None
 
@@ -470,6 +497,8 @@ class TrainStep:
         if self.world_size == 1:
             return
         lo = self._reduced_upto
+        if self.comm_ctas:
+            L.set_sm_budget(0)               # backward is over: the optimiser kernels wait for the exchange anyway
         all_reduce_flat(self.flat.G[lo:] if lo else self.flat.G, self.world_size, self.pg, self.comm_stream)
         self._reduced_upto = 0
 
@@ -510,6 +539,8 @@ class TrainStep:
         finally:
             if getattr(self.model, "_dvla_grad_marks", None) is not None:
                 self.model._dvla_grad_marks = None       # a bare forward_backward() outside the step must never reduce
+            if self.comm_ctas:
+                L.set_sm_budget(0)
         if exchange:
             self.all_reduce_grads()
         if self.per_micro_clip:
@@ -600,56 +631,102 @@ def synthetic_batch(cfg: StepConfig, batch_size, device, seed=1234, heads=None, 
     return {k: v.to(device) for k, v in out.items()}
 
 
-def batch_from_tuple(batch_calvin, device, dtype=torch.bfloat16):
-    """The 13-tuple of the reference's collator (data_utils.py:1395-1397) -> the dict used here (train_utils.py:99-123)."""
-    def mv(t):
-        return None if t is None else t.to(device, dtype=dtype, non_blocking=True)
+def batch_to_host_dict(batch_calvin):
+    """The 13-tuple of the reference's collator (data_utils.py:1395-1397) -> the dict of HOST tensors used here
+    (train_utils.py:99-123 picks the same entries)."""
     tr = batch_calvin[12] or {}
-    out = dict(images_primary=mv(batch_calvin[0]), text=batch_calvin[1].to(device, non_blocking=True),
-               actions=mv(batch_calvin[2]), images_wrist=mv(batch_calvin[3]), states=mv(batch_calvin[4]))
+    out = dict(images_primary=batch_calvin[0], text=batch_calvin[1], actions=batch_calvin[2], images_wrist=batch_calvin[3],
+               states=batch_calvin[4])
     for key, idx in (("depth_primary", 6), ("depth_wrist", 7), ("dino_primary", 8), ("dino_wrist", 9),
                      ("sam_primary", 10), ("sam_wrist", 11)):
         if batch_calvin[idx] is not None:
-            out[key] = mv(batch_calvin[idx])
+            out[key] = batch_calvin[idx]
     if "tracks" in tr:
-        out["tracks"], out["tracks_gripper"] = mv(tr["tracks"]), mv(tr["tracks_gripper"])
+        out["tracks"], out["tracks_gripper"] = tr["tracks"], tr["tracks_gripper"]
     return out
 
 
-def prefetch_to_device(loader, device, convert):
-    """Iterate `loader`, yielding `convert(host_batch)` (a dict of device tensors) one batch AHEAD of the consumer: the
-    host->device copies (and dtype casts) of batch i+1 are enqueued on a copy stream while batch i is being consumed on the
-    current stream, so a step's input transfer (193 MB at C2, ~3 ms over PCIe) hides behind the previous step's kernels.
-    `convert` must issue its copies with non_blocking=True from pinned host memory to overlap.  On a CPU device this is a
-    plain map (host logic is testable without a GPU)."""
+def batch_from_tuple(batch_calvin, device, dtype=torch.bfloat16):
+    """13-tuple -> dict of device tensors (floating point entries cast to `dtype` ON THE DEVICE: a cross-device copy with a
+    dtype change would convert on the host first)."""
+    out = {}
+    for k, v in batch_to_host_dict(batch_calvin).items():
+        d = v.to(device, non_blocking=True)
+        out[k] = d.to(dtype) if d.is_floating_point() else d
+    return out
+
+
+class _DeviceSlot:
+    """One persistent set of device input buffers of the prefetcher (+ staging buffers for entries whose host dtype differs)."""
+
+    def __init__(self):
+        self.bufs, self.stage, self.consumed = {}, {}, None
+
+    def fill(self, host, device, dtype):
+        for k, v in host.items():
+            want = dtype if v.is_floating_point() else v.dtype
+            buf = self.bufs.get(k)
+            if buf is None or buf.shape != v.shape or buf.dtype != want:
+                buf = self.bufs[k] = torch.empty(v.shape, dtype=want, device=device)
+            if v.dtype == want:
+                buf.copy_(v, non_blocking=True)
+            else:                                   # H2D in the host dtype, cast on the device
+                st = self.stage.get(k)
+                if st is None or st.shape != v.shape or st.dtype != v.dtype:
+                    st = self.stage[k] = torch.empty(v.shape, dtype=v.dtype, device=device)
+                st.copy_(v, non_blocking=True)
+                buf.copy_(st)
+        for k in [k for k in self.bufs if k not in host]:
+            del self.bufs[k]
+        return dict(self.bufs)
+
+
+def prefetch_to_device(loader, device, to_host_dict=None, dtype=torch.bfloat16, slots=2):
+    """Iterate `loader`, yielding each batch as a dict of DEVICE tensors one batch AHEAD of the consumer: the host->device
+    copies of batch i+1 run on a copy stream while batch i is being consumed on the current stream, so a step's input transfer
+    (193 MB at C2, ~3.5 ms over PCIe 5 x16) hides behind the previous step's kernels.
+
+    `to_host_dict(item)` maps a loader item to a dict of host tensors (default: the item itself); pinned host memory is
+    needed for the copy to be asynchronous.  The device buffers are `slots` persistent sets reused round-robin (no allocator
+    traffic, no cudaMalloc in steady state): a yielded dict stays valid until the consumer has asked for `slots - 1` more
+    batches -- consume it (or copy it) before that, as the training loop and the CUDA-graph step's static-buffer copy do.
+    Floating-point entries arrive as `dtype`.  On a CPU device this is a plain map (host logic is testable without a GPU)."""
     device = torch.device(device) if not isinstance(device, torch.device) else device
+    to_host_dict = to_host_dict or (lambda item: item)
     if device.type != "cuda":
-        for host in loader:
-            yield convert(host)
+        for item in loader:
+            yield {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in to_host_dict(item).items()}
         return
     copy_stream = torch.cuda.Stream(device)
     it = iter(loader)
+    ring = [_DeviceSlot() for _ in range(max(2, slots))]
 
-    def stage():
+    def stage(i):
         try:
-            host = next(it)
+            item = next(it)
         except StopIteration:
             return None
+        slot = ring[i % len(ring)]
         with torch.cuda.stream(copy_stream):
-            dev = convert(host)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return dev, ev
+            if slot.consumed is not None:
+                copy_stream.wait_event(slot.consumed)      # the step that read this slot's buffers has finished
+            dev = slot.fill(to_host_dict(item), device, dtype)
+            ready = torch.cuda.Event()
+            ready.record(copy_stream)
+        return dev, ready, slot
 
-    nxt = stage()
+    i = 0
+    nxt = stage(i)
+    prev_slot = None
     while nxt is not None:
-        dev, ev = nxt
+        dev, ready, slot = nxt
         cur = torch.cuda.current_stream(device)
-        cur.wait_event(ev)
-        for t in dev.values():
-            if isinstance(t, torch.Tensor) and t.is_cuda:
-                t.record_stream(cur)          # allocated on the copy stream, consumed on the compute stream
-        nxt = stage()                         # batch i+1 starts moving before batch i is handed out
+        if prev_slot is not None:                          # everything enqueued so far includes the consumer of the previous batch
+            prev_slot.consumed = cur.record_event()
+        cur.wait_event(ready)
+        i += 1
+        nxt = stage(i)                                     # batch i+1 starts moving before batch i is handed out
+        prev_slot = slot
         yield dev
 
 
@@ -675,7 +752,7 @@ def train_one_epoch_calvin(args, model, epoch, calvin_loader, optimizer, lr_sche
     accum = args.gradient_accumulation_steps
     state.micro = 0           # the reference counts accumulation windows from the start of each epoch (:602)
     graphed = getattr(core, "_dvla_graphed_step", None)
-    for num_steps, batch in enumerate(prefetch_to_device(calvin_loader, dev, lambda bc: batch_from_tuple(bc, dev))):
+    for num_steps, batch in enumerate(prefetch_to_device(calvin_loader, dev, batch_to_host_dict)):
         data_time_m.update(time.time() - end)
         lr = lr_scheduler.get_last_lr()[0] if lr_scheduler is not None else args.learning_rate
         if use_graph and graphed is None and state.total_micro > 0:

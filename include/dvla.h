@@ -205,6 +205,21 @@ int dvla_adamw(const dvla_adamw_args* args, void* stream);
  * (clip_grad_norm_ on .grad that keeps accumulating):  g *= grad_scale * min(1, max_norm / (sqrt(sumsq)*grad_scale + 1e-6)). */
 int dvla_grad_clip_scale(void* g_bf16, int64_t n, const float* sumsq, float max_norm, float grad_scale, void* stream);
 
+/* SM budget of the persistent GEMM kernels (one CTA / CTA pair per SM).  0 = all SMs (default).  The data-parallel train
+ * step lowers it by the number of CTAs the NCCL all-reduce occupies while gradient exchange overlaps the backward pass
+ * (train.py:173 DDP overlap), so that every GEMM CTA is resident at once.  Returns the previous value.  Process-wide. */
+int dvla_set_sm_budget(int n_sms);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Workspace sizes (bytes) of the ops that need caller-provided scratch -- the library never allocates device memory:
+ *   attn_bwd : `delta` fp32 [B, H, Lq]  (rowsum(dO * O), FlashAttention-2 backward)
+ *   silog    : `stats` fp32 [2]         (sum d, sum d^2; zeroed by the caller before dvla_silog_stats)
+ *   gemm     : 0                        (split-K partial sums are reduced in place with red.global.add)
+ * ------------------------------------------------------------------------------------------------------------- */
+int64_t dvla_attn_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Lq);
+int64_t dvla_silog_workspace_bytes(void);
+int64_t dvla_gemm_workspace_bytes(const dvla_gemm_args* args);
+
 #ifdef __cplusplus
 }
 #endif

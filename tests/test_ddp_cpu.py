@@ -56,32 +56,39 @@ def test_rank_seeds_shard_the_data():
 
 
 def test_gradient_segments_follow_backward_order():
-    """The flat gradient buffer is all-reduced in three pieces while backward runs (TrainStep._reduce_segment): segment 0
-    must only hold parameters used AFTER the backbone, segment 1 only the second half of the backbone.  A parameter that
-    feeds the backbone (projectors, resampler, query tokens, position embedding) in an early segment would be reduced
-    before its gradient exists."""
-    from dreamvla_b200.utils.train_utils import EARLY_GRAD_PREFIXES, grad_segment
+    """The flat gradient buffer is all-reduced in pieces while backward runs (TrainStep._reduce_segment): segment 0 must only
+    hold parameters used AFTER the backbone, segment k only backbone layers at or above the k-th cut, and nothing that feeds
+    the backbone (projectors, resampler, query tokens, position embedding) may sit before the last segment -- it would be
+    reduced before its gradient exists."""
+    import re
+    from dreamvla_b200.utils.train_utils import BACKBONE_CUTS, EARLY_GRAD_PREFIXES, backbone_cut_layers, grad_segment
     from tests import synth
     from tests.state_template import build_template
-    cfg = dict(synth.CASES["calvin_allheads"])
-    names = list(build_template(cfg).keys())
-    n_layers = cfg["transformer_layers"]
-    seg = {n: grad_segment(n, n_layers) for n in names}
-    feeds_backbone = ("perceiver_resampler.", "text_projector", "state_projector", "arm_state_encoder", "gripper_state_encoder",
-                      "image_primary_projector", "image_wrist_projector", "cls_token_primary_projector",
-                      "cls_token_wrist_projector", "obs_tokens", "depth_tokens", "dino_feat_tokens", "sam_feat_tokens",
-                      "trajectory_tokens", "action_pred_token", "transformer_backbone_position_embedding",
-                      "embedding_layer_norm", "vision_encoder.", "clip_model.")
-    for n in names:
-        if n.startswith(feeds_backbone):
-            assert seg[n] == 2, n
-        m = __import__("re").match(r"transformer_backbone\.h\.(\d+)\.", n)
-        if m:
-            assert seg[n] == (1 if int(m.group(1)) >= n_layers // 2 else 2), n
-        if seg[n] == 0:
-            assert n.startswith(EARLY_GRAD_PREFIXES) and "tokens" not in n.split(".")[0].replace("mask_token", ""), n
-    assert any(s == 0 for s in seg.values()) and any(s == 1 for s in seg.values())
-    assert seg["transformer_backbone.ln_f.weight"] == 1
+    assert backbone_cut_layers(24) == [18, 12, 6] and backbone_cut_layers(2) == [1] and backbone_cut_layers(1) == []
+    for n_layers in (24, 2):
+        cfg = dict(synth.CASES["calvin_allheads"], transformer_layers=n_layers)
+        names = list(build_template(cfg).keys())
+        cuts = backbone_cut_layers(n_layers)
+        last = len(cuts) + 1
+        seg = {n: grad_segment(n, n_layers) for n in names}
+        feeds_backbone = ("perceiver_resampler.", "text_projector", "state_projector", "arm_state_encoder", "gripper_state_encoder",
+                          "image_primary_projector", "image_wrist_projector", "cls_token_primary_projector",
+                          "cls_token_wrist_projector", "obs_tokens", "depth_tokens", "dino_feat_tokens", "sam_feat_tokens",
+                          "trajectory_tokens", "action_pred_token", "transformer_backbone_position_embedding",
+                          "embedding_layer_norm", "vision_encoder.", "clip_model.")
+        for n in names:
+            if n.startswith(feeds_backbone):
+                assert seg[n] == last, n
+            m = re.match(r"transformer_backbone\.h\.(\d+)\.", n)
+            if m:
+                layer = int(m.group(1))
+                want = next((k + 1 for k, c in enumerate(cuts) if layer >= c), last)
+                assert seg[n] == want, n
+            if seg[n] == 0:
+                assert n.startswith(EARLY_GRAD_PREFIXES) and "tokens" not in n.split(".")[0].replace("mask_token", ""), n
+        assert {0, 1, last} <= set(seg.values())
+        assert seg["transformer_backbone.ln_f.weight"] == 1
+    assert BACKBONE_CUTS >= 1
 
 
 def test_on_grad_ready_fires_in_backward_completion_order():
@@ -114,6 +121,7 @@ def test_prefetch_iterator_host_logic():
         for i in range(7):
             seen.append(i)
             yield {"x": torch.full((2,), float(i))}
-    out = [int(b["x"][0]) for b in prefetch_to_device(loader(), "cpu", lambda hb: {k: v * 2 for k, v in hb.items()})]
-    assert out == [0, 2, 4, 6, 8, 10, 12] and seen == list(range(7))
-    assert list(prefetch_to_device(iter(()), "cpu", lambda hb: hb)) == []
+    got = list(prefetch_to_device(loader(), "cpu", lambda hb: {k: v * 2 for k, v in hb.items()}))
+    assert [int(b["x"][0]) for b in got] == [0, 2, 4, 6, 8, 10, 12] and seen == list(range(7))
+    assert all(b["x"].dtype == torch.bfloat16 for b in got)           # floating-point entries arrive in the step's dtype
+    assert list(prefetch_to_device(iter(()), "cpu")) == []

@@ -153,17 +153,22 @@ def test_graph_replay_matches_eager(dev):
 
 def test_prefetch_to_device_delivers_every_batch(dev):
     """The copy-stream input iterator (train_one_epoch_calvin, bench.py e2e): batches arrive complete, in order, as device
-    tensors, while the consumer keeps the compute stream busy."""
+    tensors in persistent double-buffered slots, while the consumer keeps the compute stream busy; fp32 host entries are cast
+    to bf16 on the device."""
     from dreamvla_b200.utils.train_utils import prefetch_to_device
     g = torch.Generator().manual_seed(3)
-    host = [{"x": torch.randn(1 << 20, generator=g).pin_memory(), "i": torch.full((4,), i).pin_memory()} for i in range(6)]
+    host = [{"x": torch.randn(1 << 20, generator=g).pin_memory(), "i": torch.full((4,), i).pin_memory(),
+             "h": torch.randn(1 << 18, generator=g).to(torch.bfloat16).pin_memory()} for i in range(7)]
     busy = torch.randn(2048, 2048, device=dev)
-    seen = []
-    for b in prefetch_to_device(iter(host), dev, lambda hb: {k: v.to(dev, non_blocking=True) for k, v in hb.items()}):
+    seen, ptrs = [], set()
+    for b in prefetch_to_device(iter(host), dev):
         busy = busy @ busy * 1e-3                       # compute-stream work the next copy overlaps with
-        assert b["x"].is_cuda and b["i"].is_cuda
-        seen.append((int(b["i"][0]), b["x"].clone()))
+        assert b["x"].is_cuda and b["i"].is_cuda and b["x"].dtype == torch.bfloat16 and b["i"].dtype == torch.int64
+        ptrs.add(b["x"].data_ptr())
+        seen.append((int(b["i"][0]), b["x"].clone(), b["h"].clone()))     # consumed before the slot is reused
     torch.cuda.synchronize()
-    assert [i for i, _ in seen] == list(range(6))
-    for (i, x), h in zip(seen, host):
-        assert torch.equal(x.cpu(), h["x"]), i
+    assert [i for i, _, _ in seen] == list(range(7))
+    assert len(ptrs) == 2                                # two persistent slots, no per-batch allocation
+    for (i, x, h), src in zip(seen, host):
+        assert torch.equal(x.cpu(), src["x"].to(torch.bfloat16)), i
+        assert torch.equal(h.cpu(), src["h"]), i

@@ -55,10 +55,12 @@ def run(overlap, steps):
 G0, P0, l0, info, ga0, pa0 = run(False, 3)
 G2, P2, l2, _, ga2, pa2 = run(False, 3)       # same thing again: the run-to-run noise floor (fp32 atomics in LN / bias grads)
 G1, P1, l1, _, ga1, pa1 = run(True, 3)
-(e0, e1), n_big, n = info
+seg_end, n_big, n = info
 if rank == 0:
-    print(f"segments: [0,{e0}) [{e0},{e1}) [{e1},{n_big}) small [{n_big},{n})")
-    for name, lo, hi in (("seg0", 0, e0), ("seg1", e0, e1), ("seg2", e1, n_big), ("small", n_big, n)):
+    print(f"segment ends: {seg_end} | last big segment ends at {n_big} | 1-D gradients up to {n}")
+    bounds = [0] + list(seg_end) + [n_big, n]
+    labels = [f"seg{i}" for i in range(len(seg_end) + 1)] + ["small"]
+    for name, lo, hi in zip(labels, bounds[:-1], bounds[1:]):
         d = (G0[lo:hi] - G1[lo:hi]).abs()
         dn = (G0[lo:hi] - G2[lo:hi]).abs()
         print(f"  reduced gradient {name}: max|plain-overlap| = {float(d.max()):.3e} ({int((d > 0).sum())} elements differ)   "

@@ -223,6 +223,78 @@ def run_ours(args):
     value = B * world / (ms_per_step / 1e3)
     final_loss = float(loss)
 
+    # ---- end-to-end: pinned host inputs -> H2D -> step -> D2H loss, every step ----
+    # measured right after the device-resident loop, in the same power / clock state (the per-shape GEMM microbenchmark of
+    # the roofline section keeps the GPU at the power cap for seconds; a region timed after it runs at lower clocks)
+    e2e = None
+    if not args.no_e2e:
+        from dreamvla_b200.utils.train_utils import prefetch_to_device
+        host = synthetic_batch(scfg, B, dev, seed=1234 + rank, heads=heads, pin=True)
+        loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+        def host_batches(n):          # the data loader of this measurement: the same pinned batch, n times
+            for _ in range(n):
+                yield host
+
+        def e2e_run(n):
+            # the public training-loop iterator (train_one_epoch_calvin uses the same one): batch i+1 is copied host->device
+            # on a copy stream while step i runs; every step still moves its own 193 MB in and its loss out
+            for dbatch in prefetch_to_device(host_batches(n), dev):
+                ls = step(dbatch)
+                loss_host.copy_(ls.reshape(1).float(), non_blocking=True)
+        # diagnostic: one batch's host->device copy alone (idle GPU), on a side stream -- what the overlap has to hide
+        cs = torch.cuda.Stream()
+        dtmp = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(cs):
+            for k, v in host.items():
+                dtmp[k].copy_(v, non_blocking=True)
+            c0.record(cs)
+            for k, v in host.items():
+                dtmp[k].copy_(v, non_blocking=True)
+            c1.record(cs)
+        torch.cuda.synchronize()
+        h2d_alone_ms = c0.elapsed_time(c1)
+        del dtmp
+        try:
+            e2e_run(3)
+        except Exception as e:  # noqa: BLE001   (keep the measurement alive: sequential copy -> step -> read-back)
+            print(f"[bench] prefetching input pipeline failed ({e!r}); measuring e2e with in-line copies", file=sys.stderr, flush=True)
+            dbuf = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+
+            def e2e_run(n):  # noqa: F811
+                for _ in range(n):
+                    for k, v in host.items():
+                        dbuf[k].copy_(v, non_blocking=True)
+                    ls = step(dbuf)
+                    loss_host.copy_(ls.reshape(1).float(), non_blocking=True)
+            e2e_run(3)
+        sync_all()
+        sampler2 = ClockSampler(local_rank) if rank == 0 else None
+        if sampler2:
+            sampler2.start()
+        t0 = time.perf_counter()
+        e0.record()
+        e2e_run(args.steps)
+        e1.record()
+        sync_all()
+        wall = (time.perf_counter() - t0) * 1e3
+        if sampler2:
+            sampler2.stop_flag.set()
+            sampler2.join()
+        t = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t) / args.steps
+        e2e = {"value": round(B * world / (e2e_ms / 1e3), 3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms, 3), "wall_ms_per_step": round(wall / args.steps, 3),
+               "h2d_alone_ms": round(h2d_alone_ms, 3), "h2d_alone_gbs": round(h2d / h2d_alone_ms / 1e6, 2),
+               "input_pipeline": "train_utils.prefetch_to_device (copy stream, 2 persistent device slots)",
+               "clocks": sampler2.summary() if sampler2 else None}
+
+    stage("e2e done")
     # ---- roofline of the dominant kernel (tcgen05 GEMM) ----------------------------------------------------------------
     # one eager fwd+bwd records every dvla_gemm launch (shape, layout, epilogue); each distinct launch is then re-issued
     # 5x back to back on the current stream between two CUDA events (no host gaps), and
@@ -287,52 +359,6 @@ def run_ours(args):
                 "step_frac_of_peak": round(cfg["tf_per_sample"] * B / (ms_per_step * 1e-3) / peak, 4)}
 
     stage("roofline done")
-    # ---- end-to-end: pinned host inputs -> H2D -> step -> D2H loss, every step ----
-    e2e = None
-    if not args.no_e2e:
-        from dreamvla_b200.utils.train_utils import prefetch_to_device
-        host = synthetic_batch(scfg, B, dev, seed=1234 + rank, heads=heads, pin=True)
-        loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
-        h2d = sum(v.numel() * v.element_size() for v in host.values())
-
-        def host_batches(n):          # the data loader of this measurement: the same pinned batch, n times
-            for _ in range(n):
-                yield host
-
-        def e2e_run(n):
-            # the public training-loop iterator (train_one_epoch_calvin uses the same one): batch i+1 is copied host->device
-            # on a copy stream while step i runs; every step still moves its own 193 MB in and its loss out
-            for dbatch in prefetch_to_device(host_batches(n), dev):
-                ls = step(dbatch)
-                loss_host.copy_(ls.reshape(1).float(), non_blocking=True)
-        try:
-            e2e_run(3)
-        except Exception as e:  # noqa: BLE001   (keep the measurement alive: sequential copy -> step -> read-back)
-            print(f"[bench] prefetching input pipeline failed ({e!r}); measuring e2e with in-line copies", file=sys.stderr, flush=True)
-            dbuf = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
-
-            def e2e_run(n):  # noqa: F811
-                for _ in range(n):
-                    for k, v in host.items():
-                        dbuf[k].copy_(v, non_blocking=True)
-                    ls = step(dbuf)
-                    loss_host.copy_(ls.reshape(1).float(), non_blocking=True)
-            e2e_run(3)
-        sync_all()
-        t0 = time.perf_counter()
-        e0.record()
-        e2e_run(args.steps)
-        e1.record()
-        sync_all()
-        wall = (time.perf_counter() - t0) * 1e3
-        t = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t) / args.steps
-        e2e = {"value": round(B * world / (e2e_ms / 1e3), 3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms, 3), "wall_ms_per_step": round(wall / args.steps, 3)}
-
-    stage("e2e done")
     cpu = None
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         cpu = cpu_baseline(args, steps=1, warm=0)

@@ -42,7 +42,8 @@ class AttnFwdArgs(C.Structure):
                 ("B", _i64), ("H", _i64), ("Lq", _i64), ("Lk", _i64),
                 ("q_sb", _i64), ("q_ss", _i64), ("q_sh", _i64), ("k_sb", _i64), ("k_ss", _i64), ("k_sh", _i64),
                 ("v_sb", _i64), ("v_ss", _i64), ("v_sh", _i64), ("o_sb", _i64), ("o_ss", _i64), ("o_sh", _i64),
-                ("mask_words", _i32), ("scale", _f32), ("dropout_p", _f32), ("dropout_seed", _u64), ("dropout_seed_ptr", _vp)]
+                ("mask_words", _i32), ("scale", _f32), ("dropout_p", _f32), ("dropout_seed", _u64), ("dropout_seed_ptr", _vp),
+                ("key_bias", _vp)]
 
 
 class AttnBwdArgs(C.Structure):
@@ -55,7 +56,7 @@ class AttnBwdArgs(C.Structure):
                 ("dq_sb", _i64), ("dq_ss", _i64), ("dq_sh", _i64), ("dk_sb", _i64), ("dk_ss", _i64), ("dk_sh", _i64),
                 ("dv_sb", _i64), ("dv_ss", _i64), ("dv_sh", _i64),
                 ("mask_words", _i32), ("scale", _f32), ("dropout_p", _f32), ("dropout_seed", _u64), ("dropout_seed_ptr", _vp),
-                ("mask_t", _vp), ("mask_t_words", _i32)]
+                ("mask_t", _vp), ("mask_t_words", _i32), ("key_bias", _vp)]
 
 
 class AdamWArgs(C.Structure):
@@ -64,12 +65,26 @@ class AdamWArgs(C.Structure):
                 ("max_norm", _f32), ("grad_scale", _f32), ("zero_grad", _i32)]
 
 
+class DitBlockWeights(C.Structure):
+    _fields_ = [(n, _vp) for n in ("qkv_w", "qkv_b", "proj_w", "proj_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+
+
+class DitSamplerArgs(C.Structure):
+    _fields_ = [("blocks", C.POINTER(DitBlockWeights))] + \
+               [(n, _i64) for n in ("depth", "hidden", "heads", "mlp", "token", "freq", "channels", "T", "batch")] + \
+               [(n, _vp) for n in ("x_w", "x_b", "t0_w", "t0_b", "t2_w", "t2_b", "z_w", "z_b", "uncondition", "pos", "final_w",
+                                   "final_b", "z", "noise", "out")] + \
+               [("timestep_map", C.POINTER(_i32)), ("sqrt_recip_alphas_cumprod", C.POINTER(_f32)),
+                ("sqrt_recipm1_alphas_cumprod", C.POINTER(_f32)), ("alphas_cumprod_prev", C.POINTER(_f32)),
+                ("n_steps", _i64), ("cfg_scale", _f32), ("workspace", _vp), ("workspace_bytes", _i64)]
+
+
 EXPORTS = [
     "dvla_version", "dvla_last_error", "dvla_launch_count", "dvla_gemm", "dvla_layernorm_fwd", "dvla_layernorm_bwd",
     "dvla_attn_fwd", "dvla_attn_bwd", "dvla_attn_mask_tiles", "dvla_colsum_accum", "dvla_accum_fp32_into_bf16",
-    "dvla_dropout", "dvla_act_bwd", "dvla_mse_loss", "dvla_cosine_loss", "dvla_silog_stats", "dvla_silog_finish",
+    "dvla_dropout", "dvla_act_bwd", "dvla_cat_broadcast", "dvla_mse_loss", "dvla_cosine_loss", "dvla_silog_stats", "dvla_silog_finish",
     "dvla_sumsq", "dvla_adamw", "dvla_grad_clip_scale", "dvla_attn_bwd_workspace_bytes", "dvla_silog_workspace_bytes",
-    "dvla_gemm_workspace_bytes", "dvla_set_sm_budget",
+    "dvla_gemm_workspace_bytes", "dvla_set_sm_budget", "dvla_dit_ddim_sample", "dvla_dit_sampler_workspace_bytes",
 ]
 
 _lib = None
@@ -90,7 +105,8 @@ def load() -> C.CDLL:
     for name in EXPORTS:
         if not hasattr(lib, name):
             raise RuntimeError(f"{LIB_PATH} does not export {name} (stale build? run `python -m dreamvla_b200.build`)")
-    for name in ("dvla_attn_bwd_workspace_bytes", "dvla_silog_workspace_bytes", "dvla_gemm_workspace_bytes"):
+    for name in ("dvla_attn_bwd_workspace_bytes", "dvla_silog_workspace_bytes", "dvla_gemm_workspace_bytes",
+                 "dvla_dit_sampler_workspace_bytes"):
         getattr(lib, name).restype = C.c_int64
     _lib = lib
     return lib
@@ -191,7 +207,7 @@ def _bsh(t):
 
 
 def attn_fwd(q, k, v, scale, mask_bits=None, tile_flags=None, dropout_p=0.0, dropout_seed=0, need_lse=True,
-             dropout_seed_ptr=None):
+             dropout_seed_ptr=None, key_bias=None):
     """q [B,Lq,H,64], k/v [B,Lk,H,64] (arbitrary batch/seq/head strides) -> o [B,Lq,H,64] contiguous, lse [B,H,Lq]."""
     _need_cuda(q, k, v)
     B, Lq, H, _ = q.shape
@@ -209,12 +225,15 @@ def attn_fwd(q, k, v, scale, mask_bits=None, tile_flags=None, dropout_p=0.0, dro
     a.mask_words = 0 if mask_bits is None else mask_bits.shape[1]
     a.scale, a.dropout_p, a.dropout_seed = float(scale), float(dropout_p), int(dropout_seed)
     a.dropout_seed_ptr = _ptr(dropout_seed_ptr)
+    if key_bias is not None:
+        assert key_bias.dtype == torch.float32 and key_bias.is_contiguous() and key_bias.numel() == Lk
+        a.key_bias = key_bias.data_ptr()
     _check(load().dvla_attn_fwd(C.byref(a), _stream()), "dvla_attn_fwd")
     return o, lse
 
 
 def attn_bwd(q, k, v, o, d_o, lse, scale, dq, dk, dv, mask_bits=None, tile_flags=None, dropout_p=0.0, dropout_seed=0,
-             dropout_seed_ptr=None, mask_bits_t=None):
+             dropout_seed_ptr=None, mask_bits_t=None, key_bias=None):
     B, Lq, H, _ = q.shape
     Lk = k.shape[1]
     ws = int(load().dvla_attn_bwd_workspace_bytes(_i64(B), _i64(H), _i64(Lq)))
@@ -238,6 +257,7 @@ def attn_bwd(q, k, v, o, d_o, lse, scale, dq, dk, dv, mask_bits=None, tile_flags
     a.dropout_seed_ptr = _ptr(dropout_seed_ptr)
     a.mask_t = _ptr(mask_bits_t)
     a.mask_t_words = 0 if mask_bits_t is None else mask_bits_t.shape[1]
+    a.key_bias = _ptr(key_bias)
     _check(load().dvla_attn_bwd(C.byref(a), _stream()), "dvla_attn_bwd")
 
 
@@ -329,3 +349,57 @@ def grad_clip_scale(g, sumsq_t, max_norm, grad_scale=1.0):
 def set_sm_budget(n_sms: int) -> int:
     """SMs the persistent GEMM kernels size their grids for (0 = all); returns the previous value."""
     return int(load().dvla_set_sm_budget(C.c_int(int(n_sms))))
+
+
+def cat_broadcast(e, m):
+    """e [n, a, C], m [b, C] (bf16, contiguous) -> [n, a + b, C] with m appended to every sequence."""
+    _need_cuda(e, m)
+    n, a, Cc = e.shape
+    b = m.shape[0]
+    assert e.is_contiguous() and m.is_contiguous() and m.shape[1] == Cc and e.dtype == m.dtype == torch.bfloat16
+    out = torch.empty((n, a + b, Cc), device=e.device, dtype=torch.bfloat16)
+    _check(load().dvla_cat_broadcast(C.c_void_p(e.data_ptr()), C.c_void_p(m.data_ptr()), C.c_void_p(out.data_ptr()), _i64(n),
+                                     _i64(a), _i64(b), _i64(Cc), _stream()), "dvla_cat_broadcast")
+    return out
+
+
+def dit_ddim_sample(net, diffusion, z, noise, cfg_scale):
+    """Fused DDIM sampler of the DiT action head (dit_sampler.cu): z bf16 [bs, T, token] condition rows, noise fp32 [bs, T, C]
+    -> fp32 [bs, T, C].  `net` is models.action_model.models.DiT, `diffusion` the respaced SpacedDiffusion."""
+    _need_cuda(z, noise)
+    bs, T, token = z.shape
+    Cc = noise.shape[-1]
+    H = net.x_embedder.linear.weight.shape[0]
+    mlp = net.blocks[0].mlp.fc1.weight.shape[0]
+    n_steps = diffusion.num_timesteps
+    blocks = (DitBlockWeights * len(net.blocks))()
+    for i, b in enumerate(net.blocks):
+        blocks[i] = DitBlockWeights(b.attn.qkv.weight.data_ptr(), b.attn.qkv.bias.data_ptr(), b.attn.proj.weight.data_ptr(),
+                                    b.attn.proj.bias.data_ptr(), b.mlp.fc1.weight.data_ptr(), b.mlp.fc1.bias.data_ptr(),
+                                    b.mlp.fc2.weight.data_ptr(), b.mlp.fc2.bias.data_ptr())
+    z = z.contiguous()
+    noise = noise.contiguous().float()
+    out = torch.empty((bs, T, Cc), device=z.device, dtype=torch.float32)
+    ws_bytes = int(load().dvla_dit_sampler_workspace_bytes(_i64(bs), _i64(T), _i64(H), _i64(mlp), _i64(n_steps)))
+    ws = torch.empty(ws_bytes, device=z.device, dtype=torch.uint8)
+    tmap = (_i32 * n_steps)(*[int(t) for t in diffusion.timestep_map])
+    f32arr = lambda a: (_f32 * n_steps)(*[float(v) for v in a])     # noqa: E731
+    a = DitSamplerArgs()
+    a.blocks = blocks
+    a.depth, a.hidden, a.heads, a.mlp, a.token = len(net.blocks), H, net.num_heads, mlp, token
+    a.freq, a.channels, a.T, a.batch = net.t_embedder.frequency_embedding_size, Cc, T, bs
+    a.x_w, a.x_b = net.x_embedder.linear.weight.data_ptr(), net.x_embedder.linear.bias.data_ptr()
+    a.t0_w, a.t0_b = net.t_embedder.mlp[0].weight.data_ptr(), net.t_embedder.mlp[0].bias.data_ptr()
+    a.t2_w, a.t2_b = net.t_embedder.mlp[2].weight.data_ptr(), net.t_embedder.mlp[2].bias.data_ptr()
+    a.z_w, a.z_b = net.z_embedder.linear.weight.data_ptr(), net.z_embedder.linear.bias.data_ptr()
+    a.uncondition, a.pos = net.z_embedder.uncondition.data_ptr(), net.positional_embedding.data_ptr()
+    a.final_w, a.final_b = net.final_layer.linear.weight.data_ptr(), net.final_layer.linear.bias.data_ptr()
+    a.z, a.noise, a.out = z.data_ptr(), noise.data_ptr(), out.data_ptr()
+    a.timestep_map = tmap
+    a.sqrt_recip_alphas_cumprod = f32arr(diffusion.sqrt_recip_alphas_cumprod)
+    a.sqrt_recipm1_alphas_cumprod = f32arr(diffusion.sqrt_recipm1_alphas_cumprod)
+    a.alphas_cumprod_prev = f32arr(diffusion.alphas_cumprod_prev)
+    a.n_steps, a.cfg_scale = n_steps, float(cfg_scale)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws_bytes
+    _check(load().dvla_dit_ddim_sample(C.byref(a), _stream()), "dvla_dit_ddim_sample")
+    return out

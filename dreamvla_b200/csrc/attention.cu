@@ -613,6 +613,13 @@ int attn_fwd_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s) {
   if (a->mask && a->mask_words * 32 < a->Lk) { set_error("attn_fwd: mask_words too small"); return DVLA_ERR_INVALID; }
   if (a->mask && !a->tile_flags) { set_error("attn_fwd: mask given without tile_flags"); return DVLA_ERR_INVALID; }
   const int mode = attn_fwd_mode();
+  if (a->key_bias) {
+    if (!attn_small_applicable(a->Lq, a->Lk, a->mask, a->dropout_p)) {
+      set_error("attn_fwd: key_bias needs the short-sequence kernels (Lq <= 32, Lk <= 64, no mask, no dropout)");
+      return DVLA_ERR_UNSUPPORTED;
+    }
+    return attn_small_fwd_dispatch(a, s);
+  }
   if (mode == 0 && attn_small_enabled() && attn_small_applicable(a->Lq, a->Lk, a->mask, a->dropout_p))
     return attn_small_fwd_dispatch(a, s);
   AttnParams p;
@@ -687,6 +694,13 @@ int attn_bwd_dispatch(const dvla_attn_bwd_args* a, cudaStream_t s) {
     p.drop_seed_ptr = a->dropout_seed_ptr;
   }
   const int bmode = attn_bwd_mode();
+  if (a->key_bias) {
+    if (!attn_small_applicable(a->Lq, a->Lk, a->mask, a->dropout_p)) {
+      set_error("attn_bwd: key_bias needs the short-sequence kernels (Lq <= 32, Lk <= 64, no mask, no dropout)");
+      return DVLA_ERR_UNSUPPORTED;
+    }
+    return attn_small_bwd_dispatch(a, s);
+  }
   if (bmode == 0 && attn_small_enabled() && attn_small_applicable(a->Lq, a->Lk, a->mask, a->dropout_p))
     return attn_small_bwd_dispatch(a, s);          // writes delta itself
   const long long rows = (long long)p.B * p.H * p.Lq;

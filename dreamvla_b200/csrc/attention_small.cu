@@ -26,6 +26,7 @@ struct SmallParams {
   bf16 *out, *dq, *dk, *dv;
   float* lse;
   float* delta;
+  const float* key_bias;        // optional [Lk], natural-log units
   int B, H, Lq, Lk;
   long long q_sb, q_ss, q_sh, k_sb, k_ss, k_sh, v_sb, v_ss, v_sh, o_sb, o_ss, o_sh;
   long long do_sb, do_ss, do_sh, dq_sb, dq_ss, dq_sh, dk_sb, dk_ss, dk_sh, dv_sb, dv_ss, dv_sh;
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(256) attn_small_fwd_kernel(const SmallParams p
     float kk[32], vv[32];
     load_half(kp + static_cast<long long>(j) * p.k_ss, kk);
     load_half(vp + static_cast<long long>(j) * p.v_ss, vv);
-    const float s = dot_half(q, kk) * sc;
+    const float s = dot_half(q, kk) * sc + (p.key_bias ? __ldg(p.key_bias + j) * SM_LOG2E : 0.f);
     const float m_new = fmaxf(m, s);
     const float corr = ex2_approx(m - m_new);           // m = -inf on the first key -> 0
     const float e = ex2_approx(s - m_new);
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(256) attn_small_bwd_dq_kernel(const SmallParam
       float kk[32], vv[32];
       load_half(kp + static_cast<long long>(j) * p.k_ss, kk);
       load_half(vp + static_cast<long long>(j) * p.v_ss, vv);
-      const float pr = ex2_approx(dot_half(q, kk) * sc - lse2);
+      const float pr = ex2_approx(dot_half(q, kk) * sc + (p.key_bias ? __ldg(p.key_bias + j) * SM_LOG2E : 0.f) - lse2);
       const float ds = pr * (dot_half(g, vv) - dl);
 #pragma unroll
       for (int d = 0; d < 32; ++d) acc[d] = fmaf(ds, kk[d], acc[d]);
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(256) attn_small_bwd_dkv_kernel(const SmallPara
 #pragma unroll
   for (int d = 0; d < 32; ++d) { dk[d] = 0.f; dv[d] = 0.f; }
   const float sc = p.scale * SM_LOG2E;
+  const float kb = p.key_bias ? __ldg(p.key_bias + j) * SM_LOG2E : 0.f;
   const long long bh = static_cast<long long>(b) * p.H + h;
   const bf16* qp = p.q + b * p.q_sb + h * p.q_sh + half * 32;
   const bf16* gp = p.d_o + b * p.do_sb + h * p.do_sh + half * 32;
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(256) attn_small_bwd_dkv_kernel(const SmallPara
     float q[32], g[32];
     load_half(qp + static_cast<long long>(i) * p.q_ss, q);
     load_half(gp + static_cast<long long>(i) * p.do_ss, g);
-    const float pr = ex2_approx(dot_half(q, kk) * sc - __ldg(p.lse + bh * p.Lq + i) * SM_LOG2E);
+    const float pr = ex2_approx(dot_half(q, kk) * sc + kb - __ldg(p.lse + bh * p.Lq + i) * SM_LOG2E);
     const float ds = pr * (dot_half(g, vv) - __ldg(p.delta + bh * p.Lq + i));
 #pragma unroll
     for (int d = 0; d < 32; ++d) { dv[d] = fmaf(pr, g[d], dv[d]); dk[d] = fmaf(ds, q[d], dk[d]); }
@@ -191,7 +193,7 @@ bool attn_small_applicable(int64_t Lq, int64_t Lk, const void* mask, float dropo
 int attn_small_fwd_dispatch(const dvla_attn_fwd_args* a, cudaStream_t s) {
   SmallParams p{};
   p.q = (const bf16*)a->q; p.k = (const bf16*)a->k; p.v = (const bf16*)a->v; p.out = (bf16*)a->o; p.lse = a->lse;
-  p.B = (int)a->B; p.H = (int)a->H; p.Lq = (int)a->Lq; p.Lk = (int)a->Lk; p.scale = a->scale;
+  p.B = (int)a->B; p.H = (int)a->H; p.Lq = (int)a->Lq; p.Lk = (int)a->Lk; p.scale = a->scale; p.key_bias = a->key_bias;
   p.q_sb = a->q_sb; p.q_ss = a->q_ss; p.q_sh = a->q_sh; p.k_sb = a->k_sb; p.k_ss = a->k_ss; p.k_sh = a->k_sh;
   p.v_sb = a->v_sb; p.v_ss = a->v_ss; p.v_sh = a->v_sh; p.o_sb = a->o_sb; p.o_ss = a->o_ss; p.o_sh = a->o_sh;
   const long long threads = 2ll * a->B * a->H * a->Lq;
@@ -204,7 +206,7 @@ int attn_small_bwd_dispatch(const dvla_attn_bwd_args* a, cudaStream_t s) {
   SmallParams p{};
   p.q = (const bf16*)a->q; p.k = (const bf16*)a->k; p.v = (const bf16*)a->v; p.o = (const bf16*)a->o; p.d_o = (const bf16*)a->d_o;
   p.dq = (bf16*)a->dq; p.dk = (bf16*)a->dk; p.dv = (bf16*)a->dv; p.lse = const_cast<float*>(a->lse); p.delta = a->delta;
-  p.B = (int)a->B; p.H = (int)a->H; p.Lq = (int)a->Lq; p.Lk = (int)a->Lk; p.scale = a->scale;
+  p.B = (int)a->B; p.H = (int)a->H; p.Lq = (int)a->Lq; p.Lk = (int)a->Lk; p.scale = a->scale; p.key_bias = a->key_bias;
   p.q_sb = a->q_sb; p.q_ss = a->q_ss; p.q_sh = a->q_sh; p.k_sb = a->k_sb; p.k_ss = a->k_ss; p.k_sh = a->k_sh;
   p.v_sb = a->v_sb; p.v_ss = a->v_ss; p.v_sh = a->v_sh; p.o_sb = a->o_sb; p.o_ss = a->o_ss; p.o_sh = a->o_sh;
   p.do_sb = a->do_sb; p.do_ss = a->do_ss; p.do_sh = a->do_sh;

@@ -45,6 +45,8 @@ int colsum_accum_dispatch(const void* x, int64_t rows, int64_t N, int64_t ld, fl
 int accum_fp32_into_bf16_dispatch(const float* src, void* dst, int64_t n, cudaStream_t s);
 int dropout_dispatch(const void* x, void* y, int64_t rows, int64_t N, int64_t ldx, int64_t ldy, float p, uint64_t seed,
                      const uint64_t* seed_ptr, cudaStream_t s);
+int cat_broadcast_dispatch(const void* e, const void* m, void* out, int64_t n, int64_t a, int64_t b, int64_t C, cudaStream_t s);
+int dit_ddim_sample_dispatch(const dvla_dit_sampler_args* a, cudaStream_t s);
 int act_bwd_dispatch(const void* dy, const void* pre, void* dx, int64_t n, int32_t act, cudaStream_t s);
 int mse_loss_dispatch(const void* pred, const void* label, const float* row_mask, int64_t rows, int64_t C, float weight,
                       float* loss_out, void* dpred, cudaStream_t s);
@@ -87,6 +89,9 @@ int dvla_dropout(const void* x, void* y, int64_t rows, int64_t N, int64_t ldx, i
                  const uint64_t* seed_ptr, void* stream) {
   return dropout_dispatch(x, y, rows, N, ldx, ldy, p, seed, seed_ptr, S(stream));
 }
+int dvla_cat_broadcast(const void* e, const void* m, void* out, int64_t n, int64_t a, int64_t b, int64_t C, void* stream) {
+  return cat_broadcast_dispatch(e, m, out, n, a, b, C, S(stream));
+}
 int dvla_act_bwd(const void* dy, const void* pre, void* dx, int64_t n, int32_t act, void* stream) {
   return act_bwd_dispatch(dy, pre, dx, n, act, S(stream));
 }
@@ -111,6 +116,7 @@ int dvla_grad_clip_scale(void* g, int64_t n, const float* sumsq, float max_norm,
   return grad_clip_scale_dispatch(g, n, sumsq, max_norm, grad_scale, S(stream));
 }
 
+int dvla_dit_ddim_sample(const dvla_dit_sampler_args* a, void* stream) { return dit_ddim_sample_dispatch(a, S(stream)); }
 int dvla_set_sm_budget(int n_sms) {
   const int prev = g_sm_budget.exchange(n_sms > 0 ? (n_sms & ~1) : 0, std::memory_order_relaxed);   // even: CTA pairs
   return prev;

@@ -413,4 +413,34 @@ int act_bwd_dispatch(const void* dy, const void* pre, void* dx, int64_t n, int32
   return DVLA_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// out[s, :a] = e[s], out[s, a:] = m: per-sequence rows followed by rows shared by every sequence (16-byte vectors)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cat_broadcast_kernel(const uint4* __restrict__ e, const uint4* __restrict__ m,
+                                                            uint4* __restrict__ out, long long n, int a, int b, int c8) {
+  const long long per_seq = static_cast<long long>(a + b) * c8;
+  const long long total = n * per_seq;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long s = i / per_seq;
+    const long long r = i - s * per_seq;
+    const long long ea = static_cast<long long>(a) * c8;
+    out[i] = r < ea ? e[s * ea + r] : __ldg(m + (r - ea));
+  }
+}
+int cat_broadcast_dispatch(const void* e, const void* m, void* out, int64_t n, int64_t a, int64_t b, int64_t C, cudaStream_t s) {
+  if (!e || !m || !out) { set_error("cat_broadcast: null pointer"); return DVLA_ERR_INVALID; }
+  if (n <= 0 || a < 0 || b <= 0 || C <= 0 || C % 8) { set_error("cat_broadcast: bad dims (C must be a multiple of 8)"); return DVLA_ERR_INVALID; }
+  if ((reinterpret_cast<uintptr_t>(e) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(out)) & 15) {
+    set_error("cat_broadcast: buffers must be 16-byte aligned"); return DVLA_ERR_INVALID;
+  }
+  const long long total = n * (a + b) * (C / 8);
+  long long blocks = (total + 256 * 4 - 1) / (256 * 4);
+  const long long cap = 16LL * num_sms();
+  if (blocks > cap) blocks = cap;
+  cat_broadcast_kernel<<<(unsigned)blocks, 256, 0, s>>>((const uint4*)e, (const uint4*)m, (uint4*)out, n, (int)a, (int)b, (int)(C / 8));
+  DVLA_CHECK_LAUNCH("cat_broadcast");
+  return DVLA_OK;
+}
+
 }  // namespace dvla

@@ -98,17 +98,28 @@ class _WorldDecoder(nn.Module):
             c[key] = bool((rows == rows[:1]).all().item())        # one host read per parameter version (before any capture)
         return c[key]
 
+    _bias_cache = {}
+
+    @staticmethod
+    def _repeat_bias(L, n_rep, device):
+        """fp32 [L]: 0 for the distinct rows, log(n_rep) for the last one -- its key counts n_rep times in every softmax."""
+        key = (L, n_rep, str(device))
+        c = _WorldDecoder._bias_cache
+        if key not in c:
+            b = torch.zeros(L, dtype=torch.float32)
+            b[-1] = float(np.log(n_rep))
+            c[key] = b.to(device)
+        return c[key]
+
     @staticmethod
     def _block_with_repeated_key(blk, x, n_per, n_rep):
-        """timm Block on x [n, n_per + 1, D] whose last row stands for n_rep identical tokens: queries are the n_per + 1
-        distinct rows, keys / values are the n_per rows plus the shared row repeated n_rep times."""
+        """timm Block on x [n, n_per + 1, D] whose last row stands for n_rep identical tokens: the n_per + 1 distinct rows are
+        the queries and the keys; the shared row's score gets + log(n_rep), which is exactly softmax over n_rep copies of it."""
         n, L, D = x.shape
         at = blk.attn
         res, h = blk.norm1.fork(x)
         qkv = at.qkv(h).view(n, L, 3, at.num_heads, at.head_dim)
-        k = torch.cat((qkv[:, :n_per, 1], qkv[:, n_per:, 1].expand(-1, n_rep, -1, -1)), dim=1)
-        v = torch.cat((qkv[:, :n_per, 2], qkv[:, n_per:, 2].expand(-1, n_rep, -1, -1)), dim=1)
-        o = ops.attention(qkv[:, :, 0], k, v, at.scale)
+        o = ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], at.scale, key_bias=_WorldDecoder._repeat_bias(L, n_rep, x.device))
         x = at.proj(o.view(n, L, D), residual=res)
         res, h = blk.norm2.fork(x)
         return blk.mlp(h, residual=res)
@@ -139,9 +150,9 @@ class _WorldDecoder(nn.Module):
         m = (mask_token + pos_emb[:, n_per:])[0]                             # [n_mask, D], sequence independent
         qkv_e = at.qkv(blk.norm1(emb))                                       # [n, n_per, 3D]
         qkv_m = at.qkv(blk.norm1(m))                                         # [n_mask, 3D]   (once)
-        qkv = torch.cat((qkv_e, qkv_m.unsqueeze(0).expand(n, -1, -1)), dim=1).view(n, n_per + n_mask, 3, at.num_heads, at.head_dim)
+        qkv = ops.cat_broadcast(qkv_e, qkv_m).view(n, n_per + n_mask, 3, at.num_heads, at.head_dim)
         o = ops.self_attention_fused(qkv, at.scale)
-        x = torch.cat((emb, m.unsqueeze(0).expand(n, -1, -1)), dim=1)        # the block's input (residual branch)
+        x = ops.cat_broadcast(emb, m)                                        # the block's input (residual branch)
         x = at.proj(o.view(n, n_per + n_mask, hidden), residual=x)
         res, h = blk.norm2.fork(x)
         x = blk.mlp(h, residual=res)
@@ -489,6 +500,8 @@ class DreamVLA(nn.Module):
             parts.append(self.action_pred_token)
         return parts
 
+    FUSED_SAMPLER = os.environ.get("DVLA_DIT_FUSED", "1") != "0"
+
     def _ddim_actions(self, feat, sample_noise, dev):
         """10-step DDIM with classifier-free guidance 1.5 (:935-987) on feat [n, action_pred_steps, D] -> [n, steps, 7]."""
         bs = feat.shape[0]
@@ -501,6 +514,13 @@ class DreamVLA(nn.Module):
         z = torch.cat([feat, uncondition], 0)
         if self.action_model.ddim_diffusion is None:
             self.action_model.create_ddim(ddim_step=10)
+        net = self.action_model.net
+        if (self.FUSED_SAMPLER and 4 * bs * self.action_pred_steps <= 24 and 2 * self.action_pred_steps <= 8
+                and net.x_embedder.linear.weight.shape[0] == 64 * net.num_heads and not torch.is_grad_enabled()):
+            # small batches (rollouts): the whole guided DDIM loop as one persistent kernel (csrc/dit_sampler.cu)
+            from .. import _lib as L
+            return L.dit_ddim_sample(net, self.action_model.ddim_diffusion, feat.to(torch.bfloat16), noise[:bs].float(),
+                                     cfg_scale).to(feat.dtype)
         samples = self.action_model.ddim_diffusion.ddim_sample_loop(
             self.action_model.net.forward_with_cfg, noise.shape, noise, clip_denoised=False,
             model_kwargs=dict(z=z, cfg_scale=cfg_scale), device=dev, eta=0.0)
@@ -548,7 +568,7 @@ class DreamVLA(nn.Module):
         return cache[key]
 
     @torch.no_grad()
-    def rollout_action(self, text_embedding, frame_tokens, sel, sample_noise=None, prune=True):
+    def rollout_action(self, text_embedding, frame_tokens, sel, sample_noise=None, prune=True, return_features=False):
         """One action for the timestep `sel` of a window (mode='test' of `forward`, restricted to what that action needs).
 
         text_embedding [1, D] (encode_text_embedding), frame_tokens [S, 35, D] (encode_frame_tokens; frames after `sel`
@@ -579,6 +599,8 @@ class DreamVLA(nn.Module):
         x = self.embedding_layer_norm(x.contiguous())
         h = self.transformer_backbone(inputs_embeds=x, attention_mask=mask)
         feat = h[:, act_rows, :].contiguous()                                                   # [1, steps, D]
+        if return_features:                                    # the backbone's action-token rows (parity tests)
+            return feat
         samples = self._ddim_actions(feat, sample_noise, dev)
         return samples[..., :6], samples[..., 6:]
 

@@ -102,11 +102,19 @@ class MaskedAutoencoderViT(nn.Module):
             nn.init.constant_(m.weight, 1.0)
 
     def _pos_rows(self, n_img):
+        """pos_embed[:, 1:] repeated per image (the residual operand of the patch-embed GEMM), cached PER BATCH SIZE: a
+        captured CUDA graph keeps the raw pointer of the tensor it saw, so an entry must outlive other batch sizes being
+        used in between (rollout wrappers run 2-image and 2S-image batches through the same model)."""
         key = (n_img, self.pos_embed.data_ptr(), self.pos_embed._version)
-        if self._pos_cache is None or self._pos_cache[0] != key:
-            rows = self.pos_embed[0, 1:, :].repeat(n_img, 1).contiguous()
-            self._pos_cache = (key, rows)
-        return self._pos_cache[1]
+        if self._pos_cache is None:
+            self._pos_cache = {}
+        rows = self._pos_cache.get(key)
+        if rows is None:
+            stale = [k for k in self._pos_cache if k[1:] != key[1:]]        # the parameter itself changed: graphs are stale too
+            for k in stale:
+                del self._pos_cache[k]
+            rows = self._pos_cache[key] = self.pos_embed[0, 1:, :].repeat(n_img, 1).contiguous()
+        return rows
 
     def forward_encoder(self, x, mask_ratio=0.0):
         """vit_mae.py:184-206 with mask_ratio == 0 (the only value DreamVLA uses)."""

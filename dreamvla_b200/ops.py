@@ -335,9 +335,37 @@ class AttnMask:
         return AttnMask(torch.ones(n, n, dtype=torch.bool).tril(), device)
 
 
+class _CatBroadcast(torch.autograd.Function):
+    """[n, a, C] per-sequence rows + [b, C] rows shared by every sequence -> [n, a + b, C]; the gradient of the shared rows
+    is the sum over sequences (column-sum kernel over the [n, b*C] view of the incoming gradient)."""
+
+    @staticmethod
+    def forward(ctx, e, m):
+        ctx.shapes = (e.shape, m.shape)
+        return L.cat_broadcast(_bf16c(e), _bf16c(m))
+
+    @staticmethod
+    def backward(ctx, dy):
+        (n, a, C), (b, _) = ctx.shapes
+        dy = _bf16c(dy)
+        de = dm = None
+        if ctx.needs_input_grad[0]:
+            de = dy[:, :a].contiguous()
+        if ctx.needs_input_grad[1]:
+            acc = torch.zeros(b * C, device=dy.device, dtype=torch.float32)
+            L.colsum_accum(dy.view(n, (a + b) * C)[:, a * C:], acc)
+            dm = acc.to(torch.bfloat16).view(b, C)
+        return de, dm
+
+
+def cat_broadcast(e, m):
+    """torch.cat((e, m.expand(n, -1, -1)), dim=1) as one kernel each way (see _CatBroadcast)."""
+    return _apply(_CatBroadcast, e, m)
+
+
 class _Attention(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, scale, mask, dropout_p):
+    def forward(ctx, q, k, v, scale, mask, dropout_p, key_bias=None):
         need = _grad_on and any(ctx.needs_input_grad)
         seed = next_seed() if dropout_p > 0 else 0
         bits = mask.bits if mask is not None else None
@@ -345,16 +373,16 @@ class _Attention(torch.autograd.Function):
         if mask is not None:
             assert mask.Lq == q.shape[1] and mask.Lk == k.shape[1], "mask shape mismatch"
         o, lse = L.attn_fwd(q, k, v, scale, bits, flags, dropout_p, seed, need_lse=need,
-                            dropout_seed_ptr=seed_counter(q.device) if dropout_p > 0 else None)
+                            dropout_seed_ptr=seed_counter(q.device) if dropout_p > 0 else None, key_bias=key_bias)
         if need:
             ctx.save_for_backward(q, k, v, o, lse)
-        ctx.meta = (scale, mask, dropout_p, seed)
+        ctx.meta = (scale, mask, dropout_p, seed, key_bias)
         return o
 
     @staticmethod
     def backward(ctx, d_o):
         q, k, v, o, lse = ctx.saved_tensors
-        scale, mask, dropout_p, seed = ctx.meta
+        scale, mask, dropout_p, seed, key_bias = ctx.meta
         d_o = _bf16c(d_o)
         # if q, k, v are slices of one fused [B, L, 3, H, 64] buffer, produce the gradient in the same fused layout
         fused = (q.dim() == 4 and q._base is not None and q._base is k._base and q._base is v._base and
@@ -369,13 +397,14 @@ class _Attention(torch.autograd.Function):
         L.attn_bwd(q, k, v, o, d_o, lse, scale, dq, dk, dv, mask.bits if mask is not None else None,
                    mask.flags if mask is not None else None, dropout_p, seed,
                    dropout_seed_ptr=seed_counter(q.device) if dropout_p > 0 else None,
-                   mask_bits_t=mask.bits_t if mask is not None else None)
-        return dq, dk, dv, None, None, None
+                   mask_bits_t=mask.bits_t if mask is not None else None, key_bias=key_bias)
+        return dq, dk, dv, None, None, None, None
 
 
-def attention(q, k, v, scale, mask: AttnMask | None = None, dropout_p: float = 0.0):
-    """q [B,Lq,H,64], k/v [B,Lk,H,64] (strided views allowed) -> [B,Lq,H,64] contiguous."""
-    return _apply(_Attention, q, k, v, float(scale), mask, float(dropout_p))
+def attention(q, k, v, scale, mask: AttnMask | None = None, dropout_p: float = 0.0, key_bias=None):
+    """q [B,Lq,H,64], k/v [B,Lk,H,64] (strided views allowed) -> [B,Lq,H,64] contiguous.
+    key_bias: optional fp32 [Lk] added to the scaled scores (log r = key counted r times); short sequences only."""
+    return _apply(_Attention, q, k, v, float(scale), mask, float(dropout_p), key_bias)
 
 
 class _FusedQKVAttention(torch.autograd.Function):

@@ -126,6 +126,10 @@ typedef struct {
   float scale;
   float dropout_p; uint64_t dropout_seed; /* attention-probability dropout (gpt2.py:272); RNG block = ((b*H+h)*Lq+i)*ceil(Lk/8)+j/8 */
   const uint64_t* dropout_seed_ptr;       /* optional device counter added to dropout_seed */
+  const float* key_bias;      /* optional fp32 [Lk]: added to the scaled score of key j before the softmax (natural-log units).
+                                 log(r) makes key j count r times -- the identical-mask-token form of a world decoder
+                                 (dreamvla_model.py:803-806 with an all-zero position embedding).  Short-sequence kernels only
+                                 (Lq <= 32, Lk <= 64, no mask, no dropout); DVLA_ERR_UNSUPPORTED otherwise. */
 } dvla_attn_fwd_args;
 int dvla_attn_fwd(const dvla_attn_fwd_args* args, void* stream);
 
@@ -146,6 +150,7 @@ typedef struct {
   const uint32_t* mask_t;     /* optional TRANSPOSED bit matrix [Lk, mask_t_words] (bit i%32 of word i/32 of row j = pair (i,j)
                                  visible); lets the tcgen05 dK/dV kernel read a key row's query bits contiguously */
   int32_t mask_t_words;
+  const float* key_bias;      /* as in dvla_attn_fwd_args (a constant: receives no gradient) */
 } dvla_attn_bwd_args;
 int dvla_attn_bwd(const dvla_attn_bwd_args* args, void* stream);
 
@@ -164,6 +169,11 @@ int dvla_accum_fp32_into_bf16(const float* src, void* dst_bf16, int64_t n, void*
  * embd dropout (gpt2.py:459) and to re-apply an epilogue dropout mask to dY in the backward. */
 int dvla_dropout(const void* x_bf16, void* y_bf16, int64_t rows, int64_t N, int64_t ldx, int64_t ldy, float p,
                  uint64_t seed, const uint64_t* seed_ptr, void* stream);
+/* out[s, :a, :] = e[s]; out[s, a:, :] = m  -- rows shared by every sequence appended to per-sequence rows (the world
+ * decoders' [query rows | mask-token rows] inputs, dreamvla_model.py:803-806).  e bf16 [n, a, C], m bf16 [b, C], out bf16
+ * [n, a+b, C], all contiguous, C % 8 == 0. */
+int dvla_cat_broadcast(const void* e_bf16, const void* m_bf16, void* out_bf16, int64_t n, int64_t a, int64_t b, int64_t C,
+                       void* stream);
 /* dx = dy * act'(pre)  */
 int dvla_act_bwd(const void* dy_bf16, const void* pre_bf16, void* dx_bf16, int64_t n, int32_t act, void* stream);
 
@@ -204,6 +214,35 @@ int dvla_adamw(const dvla_adamw_args* args, void* stream);
 /* In-place clip of the accumulated gradient, every micro-step, as utils/train_utils.py:599-600 does
  * (clip_grad_norm_ on .grad that keeps accumulating):  g *= grad_scale * min(1, max_norm / (sqrt(sumsq)*grad_scale + 1e-6)). */
 int dvla_grad_clip_scale(void* g_bf16, int64_t n, const float* sumsq, float max_norm, float grad_scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Fused action sampler: the DDIM loop of the DiT action head with classifier-free guidance as ONE persistent cooperative
+ * kernel (replaces dreamvla_model.py:935-987 -> gaussian_diffusion.py:609-689 -> models.py:253-268 for small batches:
+ * rows = 2 * batch * 2T <= 24).  Every pointer is device memory, weights are bf16 nn.Linear layouts [out, in].
+ * Schedule tables are HOST arrays of n_steps entries (respaced DDIM: timestep_map[i] is the original timestep of step i).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void *qkv_w, *qkv_b, *proj_w, *proj_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b;   /* blocks.N.{attn.qkv, attn.proj, mlp.fc1, mlp.fc2} */
+} dvla_dit_block_weights;
+typedef struct {
+  const dvla_dit_block_weights* blocks;  /* HOST array [depth] */
+  int64_t depth, hidden, heads, mlp, token, freq, channels, T, batch;
+  const void *x_w, *x_b;                 /* x_embedder.linear [hidden, channels], [hidden] */
+  const void *t0_w, *t0_b, *t2_w, *t2_b; /* t_embedder.mlp.{0,2}: [hidden, freq], [hidden], [hidden, hidden], [hidden] */
+  const void *z_w, *z_b, *uncondition;   /* z_embedder.linear [hidden, token], [hidden]; z_embedder.uncondition [token] */
+  const void *pos;                       /* positional_embedding [2T, hidden] */
+  const void *final_w, *final_b;         /* final_layer.linear [channels, hidden], [channels] */
+  const void* z;                         /* bf16 [batch, T, token]: condition features (the backbone's action-token rows) */
+  const float* noise;                    /* fp32 [batch, T, channels]: DDIM start noise */
+  float* out;                            /* fp32 [batch, T, channels] */
+  const int32_t* timestep_map;           /* HOST [n_steps] */
+  const float *sqrt_recip_alphas_cumprod, *sqrt_recipm1_alphas_cumprod, *alphas_cumprod_prev;   /* HOST [n_steps] */
+  int64_t n_steps;
+  float cfg_scale;
+  void* workspace; int64_t workspace_bytes;   /* >= dvla_dit_sampler_workspace_bytes(...) */
+} dvla_dit_sampler_args;
+int64_t dvla_dit_sampler_workspace_bytes(int64_t batch, int64_t T, int64_t hidden, int64_t mlp, int64_t n_steps);
+int dvla_dit_ddim_sample(const dvla_dit_sampler_args* args, void* stream);
 
 /* SM budget of the persistent GEMM kernels (one CTA / CTA pair per SM).  0 = all SMs (default).  The data-parallel train
  * step lowers it by the number of CTAs the NCCL all-reduce occupies while gradient exchange overlaps the backward pass

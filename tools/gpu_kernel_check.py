@@ -11,6 +11,7 @@ import math
 import sys
 import time
 
+import numpy as np
 import torch
 
 sys.path.insert(0, __file__.rsplit("/tools/", 1)[0])
@@ -319,6 +320,40 @@ def group_attn():
     attn_case(2, 16, 1290, 1290, True, fused_qkv=True, timeit=True)
     attn_case(40, 12, 197, 197, False, fused_qkv=True, timeit=True)
     attn_case(40, 16, 265, 265, False, fused_qkv=True, timeit=True)
+    # key_bias = log(r): the last key counted r times == attention over r explicit copies of it (identical-mask-row decoders)
+    g = torch.Generator(device="cpu").manual_seed(21)
+    Bq, Hq, Lx, rep = 3, 2, 10, 256
+    q = torch.randn(Bq, Lx, Hq, 64, generator=g).to(dev, torch.bfloat16)
+    k = torch.randn(Bq, Lx, Hq, 64, generator=g).to(dev, torch.bfloat16)
+    v = torch.randn(Bq, Lx, Hq, 64, generator=g).to(dev, torch.bfloat16)
+    bias = torch.zeros(Lx, device=dev, dtype=torch.float32)
+    bias[-1] = float(np.log(rep))
+    o, lse = L.attn_fwd(q, k, v, 0.125, key_bias=bias)
+    qr, kr, vr = (t.detach().float().requires_grad_(True) for t in (q, k, v))
+    kx = torch.cat((kr[:, :-1], kr[:, -1:].expand(-1, rep, -1, -1)), dim=1)
+    vx = torch.cat((vr[:, :-1], vr[:, -1:].expand(-1, rep, -1, -1)), dim=1)
+    oref = attn_ref(qr, kx, vx, 0.125, None)
+    report("attn key_bias=log(256) fwd vs 256 explicit copies", rel(o, oref), 6e-3)
+    d_o = torch.randn(Bq, Lx, Hq, 64, generator=g).to(dev, torch.bfloat16)
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    L.attn_bwd(q, k, v, o, d_o, lse, 0.125, dq, dk, dv, key_bias=bias)
+    oref.backward(d_o.float())
+    # the 256-fold key takes ~all of the probability mass: dS = P (dP - delta) is a difference of nearly equal numbers and
+    # delta = rowsum(dO * O) is formed from the bf16-ROUNDED output (FlashAttention-2 backward), hence the wider bar
+    report("attn key_bias dq", rel(dq, qr.grad), 3e-2)
+    report("attn key_bias dk (copies summed)", rel(dk, kr.grad), 3e-2)
+    report("attn key_bias dv (copies summed)", rel(dv, vr.grad), 1e-2)
+    # cat_broadcast fwd / bwd
+    e = torch.randn(7, 9, 3072, generator=g).to(dev, torch.bfloat16).requires_grad_(True)
+    m = torch.randn(196, 3072, generator=g).to(dev, torch.bfloat16).requires_grad_(True)
+    from dreamvla_b200 import ops as _ops
+    y = _ops.cat_broadcast(e, m)
+    yref = torch.cat((e, m.unsqueeze(0).expand(7, -1, -1)), dim=1)
+    report("cat_broadcast fwd (exact)", 0.0 if torch.equal(y, yref) else 1.0, 0.5)
+    gy = torch.randn(7, 205, 3072, generator=g).to(dev, torch.bfloat16)
+    y.backward(gy)
+    report("cat_broadcast d(e) (exact)", 0.0 if torch.equal(e.grad, gy[:, :9]) else 1.0, 0.5)
+    report("cat_broadcast d(m) = sum over sequences", rel(m.grad, gy[:, 9:].float().sum(0)), 5e-3)
     # dropout: statistical check (mean preserved) + fwd/bwd consistency via finite structure
     g = torch.Generator(device="cpu").manual_seed(5)
     q = torch.randn(2, 128, 4, 64, generator=g).to(dev, torch.bfloat16)

@@ -202,11 +202,16 @@ def run_ours(args):
     n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    cuprof = bool(os.environ.get("DVLA_BENCH_CUPROF"))      # `ncu --profile-from-start off`: profile exactly the timed steps
+    if cuprof:
+        torch.cuda.cudart().cudaProfilerStart()
     e0.record()
     for _ in range(args.steps):
         loss = step(batch)
     e1.record()
     sync_all()
+    if cuprof:
+        torch.cuda.cudart().cudaProfilerStop()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - n0
     if graphed:   # replays do not pass through the host-side counter: kernels recorded per step x replays

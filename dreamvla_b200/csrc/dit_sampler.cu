@@ -17,6 +17,7 @@
 // residual stream in bf16), so results agree with it to bf16 rounding, not bit for bit (tests/test_rollout_gpu.py).
 #include <cooperative_groups.h>
 
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -71,42 +72,65 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
 }
 
 // out(m, n) = sum_k Xs[m][k] * W[n][k] (+ bias[n]) for every column n owned by this warp; Xs: shared, bf16, [M][K], K % 8 == 0.
-// epi(m, n, value) is called by lane m (m < M) once per owned column.
+// epi(m, n, value) is called by lane m (m < M) once per owned column.  A warp works on TWO columns at a time (the staged
+// activations are read once for both) and issues the weight loads of four 8-element chunks per column before using them:
+// the kernel is a weight-streaming loop whose only latency hiding is loads in flight.
 template <typename Epi>
 __device__ __forceinline__ void skinny_gemm(const bf16* __restrict__ Xs, int M, int K, const bf16* __restrict__ W,
                                             const bf16* __restrict__ bias, int N, Epi epi) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x * DS_WARPS + warp, nw = gridDim.x * DS_WARPS;
   const int chunks = K >> 3;
-  for (int n = gw; n < N; n += nw) {
-    float acc[DS_MAXM];
+  for (int n0 = gw; n0 < N; n0 += 2 * nw) {
+    const int n1 = n0 + nw;
+    const bool two = n1 < N;
+    float acc0[DS_MAXM], acc1[DS_MAXM];
 #pragma unroll
-    for (int m = 0; m < DS_MAXM; ++m) acc[m] = 0.f;
-    const uint4* wrow = reinterpret_cast<const uint4*>(W + static_cast<long long>(n) * K);
-    for (int c = lane; c < chunks; c += 32) {
-      float w[8];
-      unpack8(__ldg(wrow + c), w);
+    for (int m = 0; m < DS_MAXM; ++m) { acc0[m] = 0.f; acc1[m] = 0.f; }
+    const uint4* w0 = reinterpret_cast<const uint4*>(W + static_cast<long long>(n0) * K);
+    const uint4* w1 = reinterpret_cast<const uint4*>(W + static_cast<long long>(two ? n1 : n0) * K);
+    for (int c0 = lane; c0 < chunks; c0 += 128) {
+      uint4 a[4], b[4];
 #pragma unroll
-      for (int m = 0; m < DS_MAXM; ++m) {
-        if (m < M) {
-          float x[8];
-          unpack8(*reinterpret_cast<const uint4*>(Xs + m * K + c * 8), x);
-          float s = 0.f;
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + 32 * u;
+        a[u] = c < chunks ? __ldg(w0 + c) : make_uint4(0, 0, 0, 0);
+        b[u] = c < chunks ? __ldg(w1 + c) : make_uint4(0, 0, 0, 0);
+      }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) s = fmaf(x[j], w[j], s);
-          acc[m] += s;
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + 32 * u;
+        if (c < chunks) {
+          float wa[8], wb[8];
+          unpack8(a[u], wa);
+          unpack8(b[u], wb);
+#pragma unroll
+          for (int m = 0; m < DS_MAXM; ++m) {
+            if (m < M) {
+              float x[8];
+              unpack8(*reinterpret_cast<const uint4*>(Xs + m * K + c * 8), x);
+              float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { s0 = fmaf(x[j], wa[j], s0); s1 = fmaf(x[j], wb[j], s1); }
+              acc0[m] += s0;
+              acc1[m] += s1;
+            }
+          }
         }
       }
     }
-    float mine = 0.f;
+    float mine0 = 0.f, mine1 = 0.f;
 #pragma unroll
     for (int m = 0; m < DS_MAXM; ++m) {
       if (m < M) {
-        const float t = warp_sum_f(acc[m]);
-        if (lane == m) mine = t;
+        const float t0 = warp_sum_f(acc0[m]), t1 = warp_sum_f(acc1[m]);
+        if (lane == m) { mine0 = t0; mine1 = t1; }
       }
     }
-    if (lane < M) epi(lane, n, mine + (bias ? __bfloat162float(bias[n]) : 0.f));
+    if (lane < M) {
+      epi(lane, n0, mine0 + (bias ? __bfloat162float(bias[n0]) : 0.f));
+      if (two) epi(lane, n1, mine1 + (bias ? __bfloat162float(bias[n1]) : 0.f));
+    }
   }
 }
 
@@ -124,8 +148,23 @@ __device__ __forceinline__ void stage_layernorm(bf16* Xs, const float* __restric
     for (int c = lane; c < H; c += 32) Xs[m * H + c] = __float2bfloat16((__ldcg(row + c) - mean) * rstd);
   }
 }
-__device__ __forceinline__ void stage_rows(bf16* Xs, const float* __restrict__ src, int n) {   // fp32 global -> bf16 shared
-  for (int i = threadIdx.x; i < n; i += DS_THREADS) Xs[i] = __float2bfloat16(__ldcg(src + i));
+__device__ __forceinline__ void stage_rows(bf16* Xs, const float* __restrict__ src, int n) {   // fp32 global -> bf16 shared, n % 4 == 0
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  uint2* d2 = reinterpret_cast<uint2*>(Xs);
+  const int n4 = n >> 2;
+  for (int i0 = threadIdx.x; i0 < n4; i0 += 4 * DS_THREADS) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * DS_THREADS;
+      v[u] = i < n4 ? __ldcg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * DS_THREADS;
+      if (i < n4) d2[i] = make_uint2(pack_bf16x2(v[u].x, v[u].y), pack_bf16x2(v[u].z, v[u].w));
+    }
+  }
 }
 
 __global__ void __launch_bounds__(DS_THREADS, 1) dit_ddim_sample_kernel(const __grid_constant__ DitSamplerParams p) {
@@ -352,8 +391,11 @@ int dit_ddim_sample_dispatch(const dvla_dit_sampler_args* a, cudaStream_t s) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
   if (!coop) { set_error("dit_ddim_sample: device has no cooperative launch"); return DVLA_ERR_UNSUPPORTED; }
+  static const int env_ctas = [] { const char* v = getenv("DVLA_DIT_CTAS"); return v ? atoi(v) : 0; }();
+  int ctas = num_sms();
+  if (env_ctas > 0 && env_ctas < ctas) ctas = env_ctas;
   void* args[] = {const_cast<DitSamplerParams*>(&p)};
-  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(dit_ddim_sample_kernel), dim3(num_sms()), dim3(DS_THREADS), args, smem, s);
+  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(dit_ddim_sample_kernel), dim3(ctas), dim3(DS_THREADS), args, smem, s);
   if (e != cudaSuccess) { set_error("dit_ddim_sample launch: %s", cudaGetErrorString(e)); return DVLA_ERR_CUDA; }
   count_launch();
   return DVLA_OK;

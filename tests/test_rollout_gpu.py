@@ -169,6 +169,7 @@ def test_libero_wrapper_gripper_width(dev, ensembling):
     cfg = synth.CPU_ONLY_CASES["libero_gripper_width"]
     S = cfg["sequence_length"]
     model = build(cfg, dev)
+    model.FUSED_SAMPLER = False          # the same sampler code in both wrappers: this test compares them bit for bit
     g = torch.Generator().manual_seed(21)
     text, _ = observations(1, seed=3)
     w = ModelWrapper(model, history_len=S, use_ensembling=ensembling, libero_eval_max_steps=16, gripper_width=True, device=dev,

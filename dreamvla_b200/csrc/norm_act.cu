@@ -1,5 +1,8 @@
 // HBM-bound row kernels: LayerNorm fwd/bwd, column sums (bias grads), dropout, activation backward, fp32->bf16 folds.
 // One warp per row, 16-byte vector accesses, grids sized against the SM count.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "../../include/dvla.h"
 
@@ -203,6 +206,103 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const bf16* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// LayerNorm backward, version 2 (D a multiple of 256, with dgamma/dbeta): the kernel above moves 2.4 TB/s on the decoders'
+// [42400, 1024] tensors (profiles/r2_ncu_hbm.txt: 346 MB in 144 us, 37 % of the HBM peak) because a row costs two dependent
+// round trips (x, dy -> reduce -> dres) and its 64 per-lane dgamma/dbeta partials cap residency at 16 warps per SM.  Here the
+// partials live in SHARED memory (one private [2][D] fp32 slab per warp, plain read-modify-write with 16-byte accesses), the
+// residual-branch gradient is fetched with x and dy (one round trip per row); 2 CTAs per SM without spills (3 would need <= 85 registers).
+// ------------------------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_v2_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                                  const bf16* __restrict__ gamma, const float* __restrict__ mean,
+                                                                  const float* __restrict__ rstd, bf16* __restrict__ dx,
+                                                                  float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                  long long rows, long long ld, const bf16* __restrict__ dres) {
+  constexpr int D = NV * 256;
+  extern __shared__ __align__(16) float ln_acc[];                  // [8 warps][2][D]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* ag = ln_acc + warp * 2 * D;
+  float* ab = ag + D;
+  for (int i = lane; i < 2 * D; i += 32) ag[i] = 0.f;
+  __syncwarp();
+  auto unpack8 = [](const uint4& u, float (&f)[8]) {
+    float2 t;
+    t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+    t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+    t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+    t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+  };
+  auto load_gamma = [&](int i, float (&g)[8]) {       // 2 KB, L1 resident: cheaper than 8 * NV registers per lane
+    if (gamma) load8(gamma + (lane + i * 32) * 8, g);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = 1.f;
+    }
+  };
+  for (long long row = static_cast<long long>(blockIdx.x) * 8 + warp; row < rows; row += static_cast<long long>(gridDim.x) * 8) {
+    uint4 xr[NV], dr[NV], rr[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const long long off = row * ld + (lane + i * 32) * 8;
+      xr[i] = __ldg(reinterpret_cast<const uint4*>(x + off));
+      dr[i] = __ldg(reinterpret_cast<const uint4*>(dy + off));
+      rr[i] = dres ? __ldg(reinterpret_cast<const uint4*>(dres + off)) : make_uint4(0, 0, 0, 0);
+    }
+    const float mu = mean[row], rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float xv[8], dv[8], gmv[8];
+      unpack8(xr[i], xv);
+      unpack8(dr[i], dv);
+      load_gamma(i, gmv);
+      const int c0 = (lane + i * 32) * 8;
+      float4 g0 = *reinterpret_cast<float4*>(ag + c0), g1 = *reinterpret_cast<float4*>(ag + c0 + 4);
+      float4 b0 = *reinterpret_cast<float4*>(ab + c0), b1 = *reinterpret_cast<float4*>(ab + c0 + 4);
+      float hh[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        hh[j] = (xv[j] - mu) * rs;
+        const float gd = dv[j] * gmv[j];
+        s1 += gd;
+        s2 = fmaf(gd, hh[j], s2);
+      }
+      g0.x = fmaf(dv[0], hh[0], g0.x); g0.y = fmaf(dv[1], hh[1], g0.y); g0.z = fmaf(dv[2], hh[2], g0.z); g0.w = fmaf(dv[3], hh[3], g0.w);
+      g1.x = fmaf(dv[4], hh[4], g1.x); g1.y = fmaf(dv[5], hh[5], g1.y); g1.z = fmaf(dv[6], hh[6], g1.z); g1.w = fmaf(dv[7], hh[7], g1.w);
+      b0.x += dv[0]; b0.y += dv[1]; b0.z += dv[2]; b0.w += dv[3];
+      b1.x += dv[4]; b1.y += dv[5]; b1.z += dv[6]; b1.w += dv[7];
+      *reinterpret_cast<float4*>(ag + c0) = g0; *reinterpret_cast<float4*>(ag + c0 + 4) = g1;
+      *reinterpret_cast<float4*>(ab + c0) = b0; *reinterpret_cast<float4*>(ab + c0 + 4) = b1;
+    }
+    s1 = warp_sum(s1) * (1.0f / D);
+    s2 = warp_sum(s2) * (1.0f / D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float xv[8], dv[8], r8[8], o[8], gmv[8];
+      unpack8(xr[i], xv);
+      unpack8(dr[i], dv);
+      unpack8(rr[i], r8);
+      load_gamma(i, gmv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float h = (xv[j] - mu) * rs;
+        o[j] = fmaf(rs, dv[j] * gmv[j] - s1 - h * s2, r8[j]);
+      }
+      store8(dx + row * ld + (lane + i * 32) * 8, o);
+    }
+  }
+  __syncthreads();
+  // fold the 8 per-warp slabs; one fp32 atomic per column per CTA
+  for (int c = threadIdx.x; c < 2 * D; c += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += ln_acc[w * 2 * D + c];
+    float* dst = c < D ? dgamma : dbeta;
+    if (dst) atomicAdd(dst + (c < D ? c : c - D), t);
+  }
+}
+
 int layernorm_fwd_dispatch(const dvla_layernorm_fwd_args* a, cudaStream_t stream) {
   if (!a || !a->x || !a->y) { set_error("layernorm_fwd: null pointer"); return DVLA_ERR_INVALID; }
   if (a->D % 8 || a->ldx % 8 || a->ldy % 8 || a->D > 1024 || a->D <= 0) {
@@ -231,6 +331,21 @@ int layernorm_bwd_dispatch(const dvla_layernorm_bwd_args* a, cudaStream_t stream
   if (a->rows <= 0) return DVLA_OK;
   const int nv = (int)((a->D + 255) / 256);
   long long blocks = (a->rows + 7) / 8;
+  static const bool v2_on = [] { const char* e = getenv("DVLA_LN_BWD"); return !(e && !strcmp(e, "v1")); }();
+  if (v2_on && a->D % 256 == 0 && (a->dgamma || a->dbeta) && a->rows >= 2048) {
+    const long long cap3 = 2LL * num_sms();
+    if (blocks > cap3) blocks = cap3;
+    const size_t smem = (size_t)8 * 2 * a->D * sizeof(float);
+#define LN_BWD2(NV) do { \
+      static const cudaError_t attr_e = cudaFuncSetAttribute(layernorm_bwd_v2_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * NV * 256 * 4); \
+      if (attr_e != cudaSuccess) { set_error("layernorm_bwd_v2 smem attr: %s", cudaGetErrorString(attr_e)); return DVLA_ERR_CUDA; } \
+      layernorm_bwd_v2_kernel<NV><<<(unsigned)blocks, 256, smem, stream>>>((const bf16*)a->dy, (const bf16*)a->x, (const bf16*)a->gamma, \
+          a->mean, a->rstd, (bf16*)a->dx, a->dgamma, a->dbeta, a->rows, a->ld, (const bf16*)a->dres); } while (0)
+    switch (nv) { case 1: LN_BWD2(1); break; case 2: LN_BWD2(2); break; case 3: LN_BWD2(3); break; default: LN_BWD2(4); break; }
+#undef LN_BWD2
+    DVLA_CHECK_LAUNCH("layernorm_bwd_v2");
+    return DVLA_OK;
+  }
   const long long cap = 2LL * num_sms();        // 2 resident blocks per SM; 2*D fp32 atomics per block at the end
   if (blocks > cap) blocks = cap;
 #define LN_BWD(NV) layernorm_bwd_kernel<NV><<<(unsigned)blocks, 256, 0, stream>>>((const bf16*)a->dy, (const bf16*)a->x, \

@@ -189,7 +189,7 @@ def group_gemm_epilogue():
 def group_norm():
     import torch.nn.functional as F
     g = torch.Generator(device="cpu").manual_seed(2)
-    for (rows, D) in [(1000, 1024), (333, 768), (77, 512), (5, 384)]:
+    for (rows, D) in [(1000, 1024), (333, 768), (77, 512), (5, 384), (4099, 1024), (2600, 768), (3000, 512)]:     # >= 2048 rows: v2 kernel
         x = (torch.randn(rows, D, generator=g) * 2 + 0.5).to(dev, torch.bfloat16)
         gm = (1 + 0.1 * torch.randn(D, generator=g)).to(dev, torch.bfloat16)
         bt = (0.1 * torch.randn(D, generator=g)).to(dev, torch.bfloat16)
@@ -212,6 +212,26 @@ def group_norm():
             if affine:
                 report(f"layernorm bwd dgamma {rows}x{D}", rel(dg, gr.grad), 8e-3)
                 report(f"layernorm bwd dbeta {rows}x{D}", rel(db, br.grad), 8e-3)
+    # the fused form the blocks use (dres + dgamma/dbeta in one launch), timed at the decoder and backbone sizes
+    for rows in (42400, 10320):
+        x = torch.randn(rows, 1024, generator=g).to(dev, torch.bfloat16)
+        gm = torch.ones(1024, device=dev, dtype=torch.bfloat16)
+        y, mean, rstd = L.layernorm_fwd(x, gm, gm, 1e-5)
+        dy = torch.randn(rows, 1024, generator=g).to(dev, torch.bfloat16)
+        dres = torch.randn(rows, 1024, generator=g).to(dev, torch.bfloat16)
+        dg, db = torch.zeros(1024, device=dev), torch.zeros(1024, device=dev)
+        dx = L.layernorm_bwd(dy, x, gm, mean, rstd, dg, db, dres)
+        xr = x.float().requires_grad_(True)
+        gr = gm.float().requires_grad_(True)
+        br = gm.float().requires_grad_(True)
+        F.layer_norm(xr, (1024,), gr, br, 1e-5).backward(dy.float())
+        e_dx, e_dg, e_db = rel(dx, xr.grad + dres.float()), rel(dg, gr.grad), rel(db, br.grad)
+        dg2, db2 = torch.zeros(1024, device=dev), torch.zeros(1024, device=dev)
+        ms = bench(lambda: L.layernorm_bwd(dy, x, gm, mean, rstd, dg2, db2, dres))
+        gbs = rows * 1024 * 2 * 4 / ms / 1e6                       # x, dy, dres read + dx written
+        report(f"layernorm bwd fused dx+dres {rows}x1024", e_dx, 8e-3, f"{ms*1e3:.1f}us {gbs:.0f} GB/s")
+        report(f"layernorm bwd fused dgamma {rows}x1024", e_dg, 8e-3)
+        report(f"layernorm bwd fused dbeta {rows}x1024", e_db, 8e-3)
     x = torch.randn(2580, 3072, generator=g).to(dev, torch.bfloat16)
     out = torch.zeros(3072, device=dev)
     L.colsum_accum(x, out)

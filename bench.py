@@ -110,6 +110,26 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def ncu_gemm_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/r2_ncu_gemm.txt, last
+    entry: M=8200 N=1024 K=4096 bias + residual, tools/prof_gemm.py) next to that launch's algorithmic bytes."""
+    path = os.path.join(ROOT, "profiles", "r2_ncu_gemm.txt")
+    try:
+        rd = wr = None
+        for line in open(path):
+            t = line.split()
+            if line.strip().startswith("DRAM read"):
+                rd = float(t[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[t[3]]
+            elif line.strip().startswith("DRAM write"):
+                wr = float(t[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[t[3]]
+        M, N, K = 8200, 1024, 4096
+        algo = 2 * (M * K + N * K + 2 * M * N) + 2 * N            # A, B, residual in, out; bias
+        return {"traffic": rd + wr, "traffic_algorithmic_bytes": algo, "traffic_launch": f"gemm M={M} N={N} K={K} bias+residual",
+                "traffic_source": "profiles/r2_ncu_gemm.txt (dram__bytes_read.sum + dram__bytes_write.sum)"}
+    except Exception:  # noqa: BLE001
+        return {"traffic": None}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -299,6 +319,51 @@ def run_ours(args):
                "input_pipeline": "train_utils.prefetch_to_device (copy stream, 2 persistent device slots)",
                "clocks": sampler2.summary() if sampler2 else None}
 
+        if os.environ.get("DVLA_E2E_PROBE") and rank == 0 and world == 1:
+            # diagnostic (stderr only): which part of the input pipeline costs device time when it runs beside the step
+            def timed(fn):
+                fn(3)
+                torch.cuda.synchronize()
+                e0.record()
+                fn(args.steps)
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / args.steps
+            dbf = {k: torch.empty(v.shape, dtype=(torch.bfloat16 if v.is_floating_point() else v.dtype), device=dev) for k, v in host.items()}
+            dst = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+
+            def resident(n):
+                for _ in range(n):
+                    step(batch)
+
+            def resident_copy_in(n):      # + the device->device copy into the graph's static inputs
+                for _ in range(n):
+                    step(dbf)
+
+            def dma_beside(n):            # + unsynchronised H2D DMA on a side stream (no cast kernels, no events)
+                for _ in range(n):
+                    with torch.cuda.stream(cs):
+                        for k, v in host.items():
+                            dst[k].copy_(v, non_blocking=True)
+                    step(batch)
+
+            def dma_cast_beside(n):       # + the fp32 -> bf16 cast kernels on the side stream
+                for _ in range(n):
+                    with torch.cuda.stream(cs):
+                        for k, v in host.items():
+                            dst[k].copy_(v, non_blocking=True)
+                            if v.is_floating_point():
+                                dbf[k].copy_(dst[k])
+                    step(batch)
+
+            def prefetch3(n):
+                for dbatch in prefetch_to_device(host_batches(n), dev, slots=3):
+                    step(dbatch)
+            for name, fn in (("resident", resident), ("resident+copy_in", resident_copy_in), ("dma_beside", dma_beside),
+                             ("dma+cast_beside", dma_cast_beside), ("prefetch(2)", e2e_run), ("prefetch(3)", prefetch3),
+                             ("resident", resident)):
+                print(f"[e2e probe] {name:18s} {timed(fn):8.3f} ms/step", file=sys.stderr, flush=True)
+
     stage("e2e done")
     # ---- roofline of the dominant kernel (tcgen05 GEMM) ----------------------------------------------------------------
     # one eager fwd+bwd records every dvla_gemm launch (shape, layout, epilogue); each distinct launch is then re-issued
@@ -357,7 +422,7 @@ def run_ours(args):
         ach = fl / (tm * 1e-3) / 1e12 if tm > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (every tcgen05 GEMM launch of one fwd+bwd)",
                 "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4),
-                "peak_source": how, "traffic": None, "launches": n_tc, "distinct_launch_shapes": len(calls),
+                "peak_source": how, **ncu_gemm_traffic(), "launches": n_tc, "distinct_launch_shapes": len(calls),
                 "gemm_ms_per_step": round(tm, 3), "gemm_share_of_step": round(tm / ms_per_step, 3),
                 "gemm_tflop_per_step": round(fl / 1e12, 3),
                 "step_model_tflops": round(cfg["tf_per_sample"] * B / (ms_per_step * 1e-3), 1),

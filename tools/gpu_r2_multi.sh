@@ -6,6 +6,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 if [ "$N" = "2" ]; then
+  CUDA_VISIBLE_DEVICES=0 DVLA_E2E_PROBE=1 timeout 300 python bench.py --steps 15 --warmup 3 --no-extras --no-cpu-baseline 2>&1 | grep -E "e2e probe|Error|Traceback" | tee gpurun_out/r2_e2e_probe.log
   DVLA_GEMM_SPLITK=0 timeout 300 $TR --master-port 29521 tools/ddp_overlap_check.py 2>&1 | grep -E "segment|reduced gradient|ranks agree|losses|max\||DDP_OVERLAP|Error|error" | cut -c1-300 | tee gpurun_out/r2_ddp_overlap_check.log
 fi
 port=29530

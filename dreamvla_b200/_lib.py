@@ -24,7 +24,8 @@ class GemmArgs(C.Structure):
     _fields_ = [("a", _vp), ("b", _vp), ("out", _vp), ("bias", _vp), ("residual", _vp), ("aux_out", _vp),
                 ("aux_in", _vp), ("M", _i64), ("N", _i64), ("K", _i64), ("lda", _i64), ("ldb", _i64), ("ldo", _i64),
                 ("ldr", _i64), ("ld_aux", _i64), ("a_mn_major", _i32), ("b_mn_major", _i32), ("act", _i32),
-                ("out_fp32", _i32), ("alpha", _f32), ("dropout_p", _f32), ("dropout_seed", _u64), ("dropout_seed_ptr", _vp)]
+                ("out_fp32", _i32), ("alpha", _f32), ("dropout_p", _f32), ("dropout_seed", _u64), ("dropout_seed_ptr", _vp),
+                ("workspace", _vp), ("workspace_bytes", _i64)]
 
 
 class LayerNormFwdArgs(C.Structure):
@@ -82,7 +83,7 @@ class DitSamplerArgs(C.Structure):
 EXPORTS = [
     "dvla_version", "dvla_last_error", "dvla_launch_count", "dvla_gemm", "dvla_layernorm_fwd", "dvla_layernorm_bwd",
     "dvla_attn_fwd", "dvla_attn_bwd", "dvla_attn_mask_tiles", "dvla_colsum_accum", "dvla_accum_fp32_into_bf16",
-    "dvla_dropout", "dvla_act_bwd", "dvla_cat_broadcast", "dvla_mse_loss", "dvla_cosine_loss", "dvla_silog_stats", "dvla_silog_finish",
+    "dvla_dropout", "dvla_act_bwd", "dvla_act_bwd_colsum", "dvla_cat_broadcast", "dvla_mse_loss", "dvla_cosine_loss", "dvla_silog_stats", "dvla_silog_finish",
     "dvla_sumsq", "dvla_adamw", "dvla_grad_clip_scale", "dvla_attn_bwd_workspace_bytes", "dvla_silog_workspace_bytes",
     "dvla_gemm_workspace_bytes", "dvla_set_sm_budget", "dvla_dit_ddim_sample", "dvla_dit_sampler_workspace_bytes",
 ]
@@ -138,6 +139,21 @@ def _need_cuda(*ts) -> None:
 # ----------------------------------------------------------------------------------------------------------------------
 # raw op wrappers (no autograd)
 # ----------------------------------------------------------------------------------------------------------------------
+_gemm_ws = {}
+
+
+def gemm_workspace(device):
+    """The GEMM scratch (fp32 partial tiles + arrival counters, include/dvla.h `dvla_gemm_args.workspace`) of the CURRENT
+    stream of `device`: one zero-initialised buffer per (device, stream), kept for the life of the process -- the kernels
+    leave it all zero again, and calls on one stream are ordered, so they can share it."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    ws = _gemm_ws.get(key)
+    if ws is None:
+        ws = _gemm_ws[key] = torch.zeros(int(load().dvla_gemm_workspace_bytes(None)), device=device, dtype=torch.uint8)
+    return ws
+
+
 def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, act=0, residual=None, aux_out=None, aux_in=None, out=None,
          out_dtype=torch.bfloat16, alpha=1.0, dropout_p=0.0, dropout_seed=0, dropout_seed_ptr=None):
     """out[M,N] = epi(alpha * A @ B^T).  a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N] if b_mn); 2-D, unit inner stride."""
@@ -171,6 +187,8 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, act=0, residual=None, aux_o
     args.dropout_p = float(dropout_p)
     args.dropout_seed = int(dropout_seed)
     args.dropout_seed_ptr = _ptr(dropout_seed_ptr)
+    ws = gemm_workspace(a.device)
+    args.workspace, args.workspace_bytes = ws.data_ptr(), ws.numel()
     _check(load().dvla_gemm(C.byref(args), _stream()), "dvla_gemm")
     return out
 
@@ -292,9 +310,17 @@ def dropout(x2d, p, seed, out=None, seed_ptr=None):
     return y
 
 
-def act_bwd(dy, pre, act):
+def act_bwd(dy, pre, act, colsum_out=None):
+    """dx = dy * act'(pre); with `colsum_out` (fp32 [N]) the column sums of dx are accumulated into it in the same pass."""
     assert dy.is_contiguous() and pre.is_contiguous()
     dx = torch.empty_like(dy)
+    if colsum_out is not None:
+        N = dy.shape[-1]
+        assert colsum_out.dtype == torch.float32 and colsum_out.numel() == N and colsum_out.is_contiguous()
+        _check(load().dvla_act_bwd_colsum(C.c_void_p(dy.data_ptr()), C.c_void_p(pre.data_ptr()), C.c_void_p(dx.data_ptr()),
+                                          _i64(dy.numel() // N), _i64(N), C.c_int32(act), C.c_void_p(colsum_out.data_ptr()),
+                                          _stream()), "dvla_act_bwd_colsum")
+        return dx
     _check(load().dvla_act_bwd(C.c_void_p(dy.data_ptr()), C.c_void_p(pre.data_ptr()), C.c_void_p(dx.data_ptr()),
                                _i64(dy.numel()), C.c_int32(act), _stream()), "dvla_act_bwd")
     return dx

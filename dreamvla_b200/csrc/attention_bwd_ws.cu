@@ -43,7 +43,7 @@ attn_bwd_dq_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int qt = gridDim.x - 1 - blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int qt = gridDim.z - 1 - blockIdx.z, h = blockIdx.x, b = blockIdx.y;   // heaviest q-tiles of ALL (b, h) first (see attention_fwd_ws.cu)
   const int q0 = qt * 128;
   const int nkt = (p.Lk + 63) / 64;
   const long long bh = static_cast<long long>(b) * p.H + h;
@@ -253,7 +253,7 @@ attn_bwd_dkv_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int kt = blockIdx.z, h = blockIdx.x, b = blockIdx.y;   // early key tiles (seen by every later frame) of ALL (b, h) first
   const int k0 = kt * 128;
   const int nqt = (p.Lq + 63) / 64;
   const long long bh = static_cast<long long>(b) * p.H + h;
@@ -502,7 +502,7 @@ int attn_bwd_ws_dispatch(const dvla_attn_bwd_args* a, const uint32_t* mask_t, in
       !okst(a->do_ss, a->do_sh, a->do_sb))
     return DVLA_ERR_UNSUPPORTED;
   if (a->mask && !mask_t) return DVLA_ERR_UNSUPPORTED;
-  if ((a->Lk + 63) / 64 > BW_MAX_T || (a->Lq + 63) / 64 > BW_MAX_T) return DVLA_ERR_UNSUPPORTED;
+  if ((a->Lk + 63) / 64 > BW_MAX_T || (a->Lq + 63) / 64 > BW_MAX_T || a->H > 65535 || a->B > 65535) return DVLA_ERR_UNSUPPORTED;
   AttnBwdTcParams p;
   memset(&p, 0, sizeof(p));
   p.dq = (bf16*)a->dq; p.dk = (bf16*)a->dk; p.dv = (bf16*)a->dv; p.lse = a->lse; p.delta = a->delta;
@@ -537,12 +537,12 @@ int attn_bwd_ws_dispatch(const dvla_attn_bwd_args* a, const uint32_t* mask_t, in
   if (!make_attn_tmap_rows(&do128, a->d_o, a->Lq, a->H, a->B, a->do_ss, a->do_sh, a->do_sb, 128, &hi)) return DVLA_ERR_CUDA;
   if (!make_attn_tmap_rows(&k64, a->k, a->Lk, a->H, a->B, a->k_ss, a->k_sh, a->k_sb, 64, &hi)) return DVLA_ERR_CUDA;
   if (!make_attn_tmap_rows(&v64, a->v, a->Lk, a->H, a->B, a->v_ss, a->v_sh, a->v_sb, 64, &hi)) return DVLA_ERR_CUDA;
-  dim3 gkv((unsigned)((k_rows + 127) / 128), (unsigned)a->H, (unsigned)a->B);
+  dim3 gkv((unsigned)a->H, (unsigned)a->B, (unsigned)((k_rows + 127) / 128));
   attn_bwd_dkv_ws_kernel<<<gkv, BW_THREADS, ATTN_DKV_WS_SMEM, s>>>(q64, k128, v128, do64, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("attn_bwd_dkv_ws launch: %s", cudaGetErrorString(e)); return DVLA_ERR_CUDA; }
   count_launch();
-  dim3 gq((unsigned)((q_rows + 127) / 128), (unsigned)a->H, (unsigned)a->B);
+  dim3 gq((unsigned)a->H, (unsigned)a->B, (unsigned)((q_rows + 127) / 128));
   attn_bwd_dq_ws_kernel<<<gq, BW_THREADS, ATTN_DQ_WS_SMEM, s>>>(q128, k64, v64, do128, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("attn_bwd_dq_ws launch: %s", cudaGetErrorString(e)); return DVLA_ERR_CUDA; }

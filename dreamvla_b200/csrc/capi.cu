@@ -35,6 +35,7 @@ int num_sms() {
 }
 
 int gemm_dispatch(const dvla_gemm_args* a, cudaStream_t stream);
+int64_t gemm_workspace_bytes();
 int layernorm_fwd_dispatch(const dvla_layernorm_fwd_args* a, cudaStream_t stream);
 int layernorm_bwd_dispatch(const dvla_layernorm_bwd_args* a, cudaStream_t stream);
 int attn_fwd_dispatch(const dvla_attn_fwd_args* a, cudaStream_t stream);
@@ -48,6 +49,8 @@ int dropout_dispatch(const void* x, void* y, int64_t rows, int64_t N, int64_t ld
 int cat_broadcast_dispatch(const void* e, const void* m, void* out, int64_t n, int64_t a, int64_t b, int64_t C, cudaStream_t s);
 int dit_ddim_sample_dispatch(const dvla_dit_sampler_args* a, cudaStream_t s);
 int act_bwd_dispatch(const void* dy, const void* pre, void* dx, int64_t n, int32_t act, cudaStream_t s);
+int act_bwd_colsum_dispatch(const void* dy, const void* pre, void* dx, int64_t rows, int64_t N, int32_t act, float* colsum,
+                            cudaStream_t s);
 int mse_loss_dispatch(const void* pred, const void* label, const float* row_mask, int64_t rows, int64_t C, float weight,
                       float* loss_out, void* dpred, cudaStream_t s);
 int cosine_loss_dispatch(const void* pred, const void* label, int64_t rows, int64_t C, float weight, float* loss_out,
@@ -95,6 +98,10 @@ int dvla_cat_broadcast(const void* e, const void* m, void* out, int64_t n, int64
 int dvla_act_bwd(const void* dy, const void* pre, void* dx, int64_t n, int32_t act, void* stream) {
   return act_bwd_dispatch(dy, pre, dx, n, act, S(stream));
 }
+int dvla_act_bwd_colsum(const void* dy, const void* pre, void* dx, int64_t rows, int64_t N, int32_t act, float* colsum,
+                        void* stream) {
+  return act_bwd_colsum_dispatch(dy, pre, dx, rows, N, act, colsum, S(stream));
+}
 int dvla_mse_loss(const void* pred, const void* label, const float* row_mask, int64_t rows, int64_t C, float weight,
                   float* loss_out, void* dpred, void* stream) {
   return mse_loss_dispatch(pred, label, row_mask, rows, C, weight, loss_out, dpred, S(stream));
@@ -123,6 +130,6 @@ int dvla_set_sm_budget(int n_sms) {
 }
 int64_t dvla_attn_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Lq) { return (B > 0 && H > 0 && Lq > 0) ? 4 * B * H * Lq : 0; }
 int64_t dvla_silog_workspace_bytes(void) { return 2 * (int64_t)sizeof(float); }
-int64_t dvla_gemm_workspace_bytes(const dvla_gemm_args* args) { (void)args; return 0; }
+int64_t dvla_gemm_workspace_bytes(const dvla_gemm_args* args) { (void)args; return gemm_workspace_bytes(); }
 
 }  // extern "C"

@@ -36,6 +36,11 @@ struct GemmParams {
   int act, out_fp32, vec_ok, staged_ok;
   int k_splits, kb_per_split;   // split-K: work unit = (tile, split), each covering kb_per_split k-blocks
   int atomic_out;               // epilogue = out += v with red.global.add.bf16x2 (split-K accumulate into a gradient)
+  // K-split TAIL (see map_unit): tiles [tail_first, total) are each cut into tail_splits k-ranges of tail_kbps k-blocks; the
+  // partial accumulators meet in an fp32 workspace and the LAST unit to arrive runs the normal epilogue on the full sum
+  int tail_first, tail_splits, tail_kbps;
+  float* tail_ws;               // [slot][16 warp regions][BN/4 columns][32 lanes] fp32, all zero between launches
+  unsigned* tail_cnt;           // [slot][16] arrival counters, all zero between launches
   float alpha;
   float drop_scale;        // 1/(1-p_eff), 0 => dropout disabled
   uint32_t drop_thresh;    // round(p*65536)
@@ -328,6 +333,87 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_acc /* tmem base + acc*
   }
 }
 
+// ---- work units ---------------------------------------------------------------------------------------------------
+// A persistent CTA (pair) walks units round-robin.  Without a tail: unit = (tile, uniform k-split).  With a tail
+// (p.tail_splits > 1): units [0, tail_first) are whole tiles -- a whole number of waves -- and the tiles that would form
+// the last, partly filled wave are cut along K so that every CTA (pair) gets ~1/tail_splits of a tile instead of a
+// few getting a whole one while the rest idle:  2.2 waves of tiles cost 2.2 tile-times instead of 3.
+struct Unit { int tile, kb0, kb1, slot; };   // slot < 0: whole tile / atomic split-K; >= 0: tail tile index
+__device__ __forceinline__ int gemm_total_units(int total_tiles, const GemmParams& p) {
+  return p.tail_splits > 1 ? p.tail_first + (total_tiles - p.tail_first) * p.tail_splits : total_tiles * p.k_splits;
+}
+__device__ __forceinline__ Unit map_unit(int unit, int total_tiles, const GemmParams& p) {
+  Unit u;
+  if (p.tail_splits > 1) {
+    if (unit < p.tail_first) { u.tile = unit; u.kb0 = 0; u.kb1 = p.num_k_blocks; u.slot = -1; return u; }
+    const int t = unit - p.tail_first, nt = total_tiles - p.tail_first;
+    u.slot = t % nt;
+    u.tile = p.tail_first + u.slot;
+    u.kb0 = (t / nt) * p.tail_kbps;
+    u.kb1 = min(p.num_k_blocks, u.kb0 + p.tail_kbps);
+    return u;
+  }
+  u.tile = unit % total_tiles;
+  u.kb0 = (unit / total_tiles) * p.kb_per_split;
+  u.kb1 = min(p.num_k_blocks, u.kb0 + p.kb_per_split);
+  u.slot = -1;
+  return u;
+}
+
+// Epilogue of one K-split tail unit for one epilogue warp.  The warp owns the same 32-row x BN/4-column region of the
+// tile in every split, so the reduction is per warp region, with no CTA-wide synchronisation:
+//   1. TMEM -> registers -> red.global.add.f32 into the region's workspace ([column][lane]: 128 contiguous bytes per warp
+//      instruction); the accumulator stage is handed back to the MMA warp as soon as it has been read;
+//   2. __threadfence, one atomicAdd on the region's arrival counter;
+//   3. the warp that arrives LAST reads the complete fp32 sum back (L2, ld.cg), zeroes workspace and counter for the
+//      next launch, and runs the ordinary fused epilogue (bias / act / dropout / residual / aux) on it -- one rounding to
+//      bf16, whatever the number of splits.
+template <int BN, typename ArriveFn>
+__device__ __forceinline__ void epilogue_tile_tail(uint32_t t_acc, uint8_t* staging, int warp, int lane, int m0, int n0,
+                                                   const GemmParams& p, int cta_slot, ArriveFn arrive_tmem_free) {
+  const int q = warp & 3;
+  const int quarter = (warp - 2) >> 2;
+  const uint32_t t_lane = t_acc + (static_cast<uint32_t>(q * 32) << 16);
+  uint8_t* stage = staging + (warp - 2) * EPI_STAGE_BYTES;
+  constexpr int CPW = BN / 4 / 32;
+  const long long region = static_cast<long long>(cta_slot) * NUM_EPI_WARPS + (warp - 2);
+  float* ws = p.tail_ws + region * (BN / 4) * 32 + lane;
+#pragma unroll 1
+  for (int ci = 0; ci < CPW; ++ci) {
+    uint32_t r[32];
+    tmem_ld_32x32(t_lane + quarter * (BN / 4) + ci * 32, r);
+    tmem_ld_wait();
+    if (ci == CPW - 1) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) arrive_tmem_free();
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      asm volatile("red.global.add.f32 [%0], %1;" :: "l"(ws + (ci * 32 + j) * 32), "f"(__uint_as_float(r[j])) : "memory");
+  }
+  __threadfence();
+  __syncwarp();
+  unsigned arrived = 0;
+  if (lane == 0) arrived = atomicAdd(p.tail_cnt + region, 1u);
+  arrived = __shfl_sync(0xffffffffu, arrived, 0);
+  if (arrived != static_cast<unsigned>(p.tail_splits - 1)) return;
+  __threadfence();
+  if (lane == 0) p.tail_cnt[region] = 0u;
+#pragma unroll 1
+  for (int ci = 0; ci < CPW; ++ci) {
+    const int c = quarter * (BN / 4) + ci * 32;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      v[j] = __ldcg(ws + (ci * 32 + j) * 32);
+      __stcg(ws + (ci * 32 + j) * 32, 0.f);
+    }
+    if (n0 + c >= p.N) continue;     // warp-uniform
+    epilogue_chunk_staged(v, stage, lane, m0 + q * 32, n0 + c, p);
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -367,7 +453,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   const int total_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int total_units = total_tiles * p.k_splits;
+  const int total_units = gemm_total_units(total_tiles, p);
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer ------------------------------------------------
@@ -375,11 +461,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int s = 0;
       uint32_t ph = 0;
       for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-        const int tile = unit % total_tiles;
-        const int m0 = (tile % p.num_m_tiles) * BM;
-        const int n0 = (tile / p.num_m_tiles) * BN;
-        const int kb0 = (unit / total_tiles) * p.kb_per_split;
-        const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
+        const Unit u = map_unit(unit, total_tiles, p);
+        const int m0 = (u.tile % p.num_m_tiles) * BM;
+        const int n0 = (u.tile / p.num_m_tiles) * BN;
+        const int kb0 = u.kb0, kb1 = u.kb1;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
@@ -413,8 +498,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        const int kb0 = (unit / total_tiles) * p.kb_per_split;
-        const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
+        const Unit u = map_unit(unit, total_tiles, p);
+        const int kb0 = u.kb0, kb1 = u.kb1;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
@@ -441,13 +526,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_ph = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-      const int tile = unit % total_tiles;
-      const int m0 = (tile % p.num_m_tiles) * BM;
-      const int n0 = (tile / p.num_m_tiles) * BN;
+      const Unit u = map_unit(unit, total_tiles, p);
+      const int m0 = (u.tile % p.num_m_tiles) * BM;
+      const int n0 = (u.tile / p.num_m_tiles) * BN;
       mbar_wait(&tfull_bar[acc], acc_ph);
       tc_fence_after();
       uint64_t* free_bar = &tempty_bar[acc];
-      epilogue_tile<BN>(tmem_base + acc * BN, staging, warp, lane, m0, n0, p, [free_bar] { mbar_arrive(free_bar); });
+      if (u.slot >= 0)
+        epilogue_tile_tail<BN>(tmem_base + acc * BN, staging, warp, lane, m0, n0, p, u.slot, [free_bar] { mbar_arrive(free_bar); });
+      else
+        epilogue_tile<BN>(tmem_base + acc * BN, staging, warp, lane, m0, n0, p, [free_bar] { mbar_arrive(free_bar); });
       acc ^= 1;
       if (acc == 0) acc_ph ^= 1;
     }
@@ -523,7 +611,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   const int num_m2 = (p.M + 2 * BM - 1) / (2 * BM);
   const int total_tiles = num_m2 * p.num_n_tiles;
-  const int total_units = total_tiles * p.k_splits;
+  const int total_units = gemm_total_units(total_tiles, p);
   const int num_clusters = gridDim.x >> 1;
   const int cluster_id = blockIdx.x >> 1;
 
@@ -532,11 +620,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       int s = 0;
       uint32_t ph = 0;
       for (int unit = cluster_id; unit < total_units; unit += num_clusters) {
-        const int tile = unit % total_tiles;
-        const int m0 = (tile % num_m2) * (2 * BM) + rank * BM;
-        const int n0 = (tile / num_m2) * BN + rank * 128;
-        const int kb0 = (unit / total_tiles) * p.kb_per_split;
-        const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
+        const Unit u = map_unit(unit, total_tiles, p);
+        const int m0 = (u.tile % num_m2) * (2 * BM) + rank * BM;
+        const int n0 = (u.tile / num_m2) * BN + rank * 128;
+        const int kb0 = u.kb0, kb1 = u.kb1;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           if (leader) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
@@ -570,8 +657,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        const int kb0 = (unit / total_tiles) * p.kb_per_split;
-        const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
+        const Unit u = map_unit(unit, total_tiles, p);
+        const int kb0 = u.kb0, kb1 = u.kb1;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
@@ -597,13 +684,17 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     int acc = 0;
     uint32_t acc_ph = 0;
     for (int unit = cluster_id; unit < total_units; unit += num_clusters) {
-      const int tile = unit % total_tiles;
-      const int m0 = (tile % num_m2) * (2 * BM) + rank * BM;
-      const int n0 = (tile / num_m2) * BN;
+      const Unit u = map_unit(unit, total_tiles, p);
+      const int m0 = (u.tile % num_m2) * (2 * BM) + rank * BM;
+      const int n0 = (u.tile / num_m2) * BN;
       mbar_wait(&tfull_bar[acc], acc_ph);
       tc_fence_after();
       uint64_t* free_bar = &tempty_bar[acc];
-      epilogue_tile<BN>(tmem_base + acc * BN, staging, warp, lane, m0, n0, p, [free_bar] { mbar_arrive_leader(free_bar); });
+      if (u.slot >= 0)
+        epilogue_tile_tail<BN>(tmem_base + acc * BN, staging, warp, lane, m0, n0, p, 2 * u.slot + static_cast<int>(rank),
+                               [free_bar] { mbar_arrive_leader(free_bar); });
+      else
+        epilogue_tile<BN>(tmem_base + acc * BN, staging, warp, lane, m0, n0, p, [free_bar] { mbar_arrive_leader(free_bar); });
       acc ^= 1;
       if (acc == 0) acc_ph ^= 1;
     }
@@ -773,7 +864,8 @@ static int launch_tc(const dvla_gemm_args* a, const GemmParams& p, cudaStream_t 
   if (!set_smem_attr_once(once, attr_err, kern, Cfg::SMEM_BYTES)) {
     set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(attr_err)); return DVLA_ERR_CUDA;
   }
-  const int tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;
+  const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
+  const int tiles = p.tail_splits > 1 ? p.tail_first + (tiles_mn - p.tail_first) * p.tail_splits : tiles_mn * p.k_splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
   cudaError_t e = cudaGetLastError();
@@ -796,7 +888,8 @@ static int launch_tc2(const dvla_gemm_args* a, const GemmParams& p, cudaStream_t
   if (!set_smem_attr_once(once, attr_err, kern, Cfg::SMEM_BYTES)) {
     set_error("cudaFuncSetAttribute(2cta smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(attr_err)); return DVLA_ERR_CUDA;
   }
-  const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * p.num_n_tiles * p.k_splits;
+  const int tiles_mn = ((p.M + 2 * BM - 1) / (2 * BM)) * p.num_n_tiles;
+  const int tiles = p.tail_splits > 1 ? p.tail_first + (tiles_mn - p.tail_first) * p.tail_splits : tiles_mn * p.k_splits;
   const int max_clusters = num_sms() / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   kern<<<2 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
@@ -822,6 +915,48 @@ static bool splitk_enabled() {
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// DVLA_GEMM_TAIL=0 disables the K-split tail / fp32 split-K reduction (every unit is then a whole tile or an atomic split)
+static bool tail_enabled() {
+  static const bool on = [] { const char* e = getenv("DVLA_GEMM_TAIL"); return !(e && !strcmp(e, "0")); }();
+  return on;
+}
+// workspace = [16384 arrival counters (64 KB)] [fp32 partial tiles: 128 x BN x 4 bytes per CTA slot]
+constexpr int64_t TAIL_CNT_BYTES = 65536;
+constexpr int64_t TAIL_WS_SLOTS = 160;               // 128 x 256 fp32 slots: covers every partial wave of 148 CTAs / 74 pairs
+int64_t gemm_workspace_bytes() { return TAIL_CNT_BYTES + TAIL_WS_SLOTS * 128 * 256 * 4; }
+
+static bool tail_fits(const dvla_gemm_args* a, long long tail_tiles, int ctas_per_tile, int bn) {
+  if (!a->workspace || (reinterpret_cast<uintptr_t>(a->workspace) & 15)) return false;
+  const long long slots = tail_tiles * ctas_per_tile;
+  return slots * NUM_EPI_WARPS * 4 <= TAIL_CNT_BYTES && TAIL_CNT_BYTES + slots * 128LL * bn * 4 <= a->workspace_bytes;
+}
+static void set_tail(GemmParams& p, const dvla_gemm_args* a, int first, int splits, int kbps) {
+  p.tail_first = first; p.tail_splits = splits; p.tail_kbps = kbps;
+  p.tail_cnt = reinterpret_cast<unsigned*>(a->workspace);
+  p.tail_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a->workspace) + TAIL_CNT_BYTES);
+}
+// The tiles of a partly filled last wave are cut along K (see map_unit).  Model, in k-block times of one tile: a unit costs
+// its k-blocks + c0 (fill / drain / epilogue); a tail unit additionally the fp32 round trip through L2 (c_fix).
+static void plan_tail(GemmParams& p, const dvla_gemm_args* a, long long total_tiles, int slots, int ctas_per_tile, int bn) {
+  if (!tail_enabled() || !p.staged_ok || p.k_splits != 1 || total_tiles <= 0) return;
+  const long long full_waves = total_tiles / slots;
+  const long long rem = total_tiles - full_waves * slots;
+  if (rem == 0) return;
+  int tsp = (int)(slots / rem);
+  if (tsp > 8) tsp = 8;
+  if (tsp > p.num_k_blocks / 4) tsp = p.num_k_blocks / 4;
+  if (tsp < 2) return;
+  const int kbps = (p.num_k_blocks + tsp - 1) / tsp;
+  tsp = (p.num_k_blocks + kbps - 1) / kbps;
+  if (tsp < 2) return;
+  const float c0 = 8.f, c_fix = 12.f;
+  const float now = (float)(full_waves + 1) * ((float)p.num_k_blocks + c0);
+  const float with_tail = (float)full_waves * ((float)p.num_k_blocks + c0) + (float)kbps + c0 + c_fix;
+  if (with_tail > 0.93f * now) return;
+  if (!tail_fits(a, rem, ctas_per_tile, bn)) return;
+  set_tail(p, a, (int)(full_waves * slots), tsp, kbps);
+}
 
 int gemm_dispatch(const dvla_gemm_args* a, cudaStream_t stream) {
   if (!a || !a->a || !a->b || !a->out) { set_error("dvla_gemm: null pointer"); return DVLA_ERR_INVALID; }
@@ -897,10 +1032,18 @@ int gemm_dispatch(const dvla_gemm_args* a, cudaStream_t stream) {
       }
     }
     if (best_s > 1) {
-      p.k_splits = best_s;
-      p.kb_per_split = (p.num_k_blocks + best_s - 1) / best_s;
-      p.atomic_out = 1;
-      p.residual = nullptr;
+      const int kbps = (p.num_k_blocks + best_s - 1) / best_s;
+      const int bn_sel = best_cfg == 2 ? 128 : 256;
+      if (tail_enabled() && tail_fits(a, tl[best_cfg], best_cfg == 0 ? 2 : 1, bn_sel)) {
+        // every tile is split; the partial sums meet in fp32 and the last unit adds the complete product to the gradient
+        // (out = residual = G): ONE bf16 rounding per accumulation instead of one per split
+        set_tail(p, a, 0, best_s, kbps);
+      } else {
+        p.k_splits = best_s;
+        p.kb_per_split = kbps;
+        p.atomic_out = 1;
+        p.residual = nullptr;
+      }
       const int key2 = (a->a_mn_major ? 2 : 0) | (a->b_mn_major ? 1 : 0);
       if (best_cfg == 0) {
         p.num_n_tiles = (p.N + 255) / 256;
@@ -934,6 +1077,7 @@ int gemm_dispatch(const dvla_gemm_args* a, cudaStream_t stream) {
     const bool big = (long long)p.M * p.N >= 256LL * 256 * 40;
     if (gemm_mode() == 2 || (big && p.N > 128 && r2 <= r1)) {
       p.num_n_tiles = (p.N + 255) / 256;
+      plan_tail(p, a, t2, sms / 2, 2, 256);
       const int key2 = (a->a_mn_major ? 2 : 0) | (a->b_mn_major ? 1 : 0);
       switch (key2) {
         case 0: return launch_tc2<false, false>(a, p, stream);
@@ -951,6 +1095,7 @@ int gemm_dispatch(const dvla_gemm_args* a, cudaStream_t stream) {
   const bool use256 = (p.N > 128) && (cost256 <= cost128);
   const int BNsel = use256 ? 256 : 128;
   p.num_n_tiles = (p.N + BNsel - 1) / BNsel;
+  plan_tail(p, a, use256 ? t256 : t128, sms, 1, BNsel);
   const int key = (use256 ? 4 : 0) | (a->a_mn_major ? 2 : 0) | (a->b_mn_major ? 1 : 0);
   switch (key) {
     case 0: return launch_tc<128, false, false>(a, p, stream);

@@ -529,6 +529,80 @@ int act_bwd_dispatch(const void* dy, const void* pre, void* dx, int64_t n, int32
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// dx = dy * act'(pre) AND colsum[c] += sum_r dx[r, c] in one pass: the bias gradient of the first MLP layer is the column
+// sum of exactly the tensor this kernel writes, so the separate colsum pass (a third read of [rows, 4D]) disappears.
+// Same block shape as colsum_kernel: 8 warps over a slab of 256 columns x a chunk of rows, each lane owns 8 columns
+// (one 16-byte vector of dy and of pre per row, 4 rows in flight), column partials in registers -> shared memory -> ONE
+// fp32 atomicAdd per column per block.  The sum is taken over the fp32 products (before the bf16 rounding of dx).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) act_bwd_colsum_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ pre,
+                                                             bf16* __restrict__ dx, long long rows, int N,
+                                                             float* __restrict__ colsum, int rows_per_block, int act) {
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ float red[8][257];
+  const int col = blockIdx.x * 256 + lane * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  auto one = [&](const uint4& a, const uint4& b, long long r) {
+    float v[8], x[8];
+    float2 f;
+    f = unpack_bf16x2(a.x); v[0] = f.x; v[1] = f.y; f = unpack_bf16x2(a.y); v[2] = f.x; v[3] = f.y;
+    f = unpack_bf16x2(a.z); v[4] = f.x; v[5] = f.y; f = unpack_bf16x2(a.w); v[6] = f.x; v[7] = f.y;
+    f = unpack_bf16x2(b.x); x[0] = f.x; x[1] = f.y; f = unpack_bf16x2(b.y); x[2] = f.x; x[3] = f.y;
+    f = unpack_bf16x2(b.z); x[4] = f.x; x[5] = f.y; f = unpack_bf16x2(b.w); x[6] = f.x; x[7] = f.y;
+    act_bwd_mul_n<8>(v, x, act);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    *reinterpret_cast<uint4*>(dx + r * N + col) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  };
+  if (col < N) {
+    long long r = r0 + warp;
+    for (; r + 24 < r1; r += 32) {
+      uint4 a[4], b[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        a[k] = __ldg(reinterpret_cast<const uint4*>(dy + (r + 8 * k) * N + col));
+        b[k] = __ldg(reinterpret_cast<const uint4*>(pre + (r + 8 * k) * N + col));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) one(a[k], b[k], r + 8 * k);
+    }
+    for (; r < r1; r += 8)
+      one(__ldg(reinterpret_cast<const uint4*>(dy + r * N + col)), __ldg(reinterpret_cast<const uint4*>(pre + r * N + col)), r);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = threadIdx.x;
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += red[w][c];
+  if (blockIdx.x * 256 + c < N) atomicAdd(colsum + blockIdx.x * 256 + c, t);
+}
+int act_bwd_colsum_dispatch(const void* dy, const void* pre, void* dx, int64_t rows, int64_t N, int32_t act, float* colsum,
+                            cudaStream_t s) {
+  if (!dy || !pre || !dx || !colsum) { set_error("act_bwd_colsum: null pointer"); return DVLA_ERR_INVALID; }
+  if (rows <= 0 || N <= 0) return DVLA_OK;
+  if (N % 8 || ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(dx)) & 15)) {
+    // unaligned / odd width: the two separate passes
+    int rc = act_bwd_dispatch(dy, pre, dx, rows * N, act, s);
+    if (rc != DVLA_OK) return rc;
+    return colsum_accum_dispatch(dx, rows, N, N, colsum, s);
+  }
+  const int bx = (int)((N + 255) / 256);
+  int by = (8 * num_sms() + bx - 1) / bx;
+  if (by > (rows + 31) / 32) by = (int)((rows + 31) / 32);
+  if (by < 1) by = 1;
+  const int rpb = (int)((rows + by - 1) / by);
+  by = (int)((rows + rpb - 1) / rpb);
+  act_bwd_colsum_kernel<<<dim3(bx, by), 256, 0, s>>>((const bf16*)dy, (const bf16*)pre, (bf16*)dx, rows, (int)N, colsum, rpb, act);
+  DVLA_CHECK_LAUNCH("act_bwd_colsum");
+  return DVLA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // out[s, :a] = e[s], out[s, a:] = m: per-sequence rows followed by rows shared by every sequence (16-byte vectors)
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) cat_broadcast_kernel(const uint4* __restrict__ e, const uint4* __restrict__ m,

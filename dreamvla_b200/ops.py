@@ -66,6 +66,15 @@ def _accum_grad_2d(param, a, b, a_mn, b_mn):
     return L.gemm(a, b, a_mn=a_mn, b_mn=b_mn)
 
 
+def _act_bwd_with_bias_grad(dz, aux, act, bias):
+    """dz * act'(aux) -> (d_pre, db, done): when the bias owns a flat fp32 gradient slot its gradient (the column sum of
+    d_pre) is accumulated by the same kernel (done=True, db=None); otherwise the caller takes the separate column sum."""
+    g32 = getattr(bias, "_dvla_grad32", None) if (bias is not None and bias.requires_grad) else None
+    if g32 is not None and dz.dim() == 2 and dz.is_contiguous():
+        return L.act_bwd(dz, aux, act, colsum_out=g32), True
+    return L.act_bwd(dz, aux, act), False
+
+
 def _accum_bias_grad(param, dy2d):
     g32 = getattr(param, "_dvla_grad32", None)
     if g32 is not None:
@@ -135,8 +144,9 @@ class _Linear(torch.autograd.Function):
         dz = dy2  # gradient w.r.t. (act output before dropout)
         if dropout_p > 0:
             dz = L.dropout(dy2, dropout_p, seed, seed_ptr=seed_counter(dy2.device))
-        if act != 0:
-            dz = L.act_bwd(dz, aux, act)      # gradient w.r.t. the pre-activation (alpha*acc + bias)
+        bias_done = False
+        if act != 0:                          # gradient w.r.t. the pre-activation (alpha*acc + bias), + the bias gradient
+            dz, bias_done = _act_bwd_with_bias_grad(dz, aux, act, bias)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             # dX[M,K] = dZ[M,N] @ W ; contraction over N.  W [N,K] -> B(n_out=k, k_contr=n) = W[n, k]: MN-major B.
@@ -148,7 +158,7 @@ class _Linear(torch.autograd.Function):
                 dw = _accum_grad_2d(weight, dz, x2, True, True) if alpha == 1.0 else None
             if alpha != 1.0:
                 raise RuntimeError("alpha != 1 with trainable weight is not supported")
-        if bias is not None and bias.requires_grad:
+        if bias is not None and bias.requires_grad and not bias_done:
             db = _accum_bias_grad(bias, dz)
         return dx, dw, db, d_res, None, None, None, None
 
@@ -197,10 +207,11 @@ class _MLP(torch.autograd.Function):
         # (dZ2 W2) * act'(pre).  The GEMM can apply act' in its epilogue (aux_in): measured +18 % GEMM time with 8 epilogue
         # warps per CTA and still no gain with 16 (104.9 vs 104.3 ms/step, profiles/r1_notes.md), so the HBM-bound
         # elementwise kernel stays the default.
+        b1_done = False
         if _FUSE_ACT_BWD:
             dh = L.gemm(dz2, w2, b_mn=not weight_kn, aux_in=aux, act=act)
-        else:
-            dh = L.act_bwd(L.gemm(dz2, w2, b_mn=not weight_kn), aux, act)
+        else:                                 # act' and the first layer's bias gradient in one pass over [rows, hidden]
+            dh, b1_done = _act_bwd_with_bias_grad(L.gemm(dz2, w2, b_mn=not weight_kn), aux, act, b1)
         dw1 = dw2 = db1 = db2 = dx = None
         if w2.requires_grad:
             dw2 = _accum_grad_2d(w2, h, dz2, True, True) if weight_kn else _accum_grad_2d(w2, dz2, h, True, True)
@@ -210,7 +221,7 @@ class _MLP(torch.autograd.Function):
             dx = L.gemm(dh, w1, b_mn=not weight_kn).view(xshape)
         if w1.requires_grad:
             dw1 = _accum_grad_2d(w1, x2, dh, True, True) if weight_kn else _accum_grad_2d(w1, dh, x2, True, True)
-        if b1 is not None and b1.requires_grad:
+        if b1 is not None and b1.requires_grad and not b1_done:
             db1 = _accum_bias_grad(b1, dh)
         return dx, dw1, db1, dw2, db2, d_res, None, None, None
 

@@ -64,6 +64,12 @@ typedef struct {
   float dropout_p;        /* 0 disables */
   uint64_t dropout_seed;  /* RNG block = m*ceil(N/8) + n/8, bit n%8 (same convention as dvla_dropout) */
   const uint64_t* dropout_seed_ptr; /* optional DEVICE counter added to dropout_seed at run time (CUDA-graph replays) */
+  /* optional scratch of >= dvla_gemm_workspace_bytes() bytes, 16-byte aligned, ALL ZERO before the first call and owned by
+   * one stream (calls on one stream may share it; every call leaves it all zero again).  With it, the output tiles that
+   * would form a partly filled last wave are cut along K and reduced in fp32 through this buffer, and split-K weight
+   * gradients are reduced in fp32 instead of with bf16 atomics.  NULL: whole tiles / bf16 red.global.add only. */
+  void* workspace;
+  int64_t workspace_bytes;
 } dvla_gemm_args;
 int dvla_gemm(const dvla_gemm_args* args, void* stream);
 
@@ -176,6 +182,11 @@ int dvla_cat_broadcast(const void* e_bf16, const void* m_bf16, void* out_bf16, i
                        void* stream);
 /* dx = dy * act'(pre)  */
 int dvla_act_bwd(const void* dy_bf16, const void* pre_bf16, void* dx_bf16, int64_t n, int32_t act, void* stream);
+/* The same, plus colsum_f32[c] += sum_r dx[r, c] in the same pass: the bias gradient of the layer whose pre-activation
+ * `pre` is (what torch's AddmmBackward computes as grad.sum(0) after GeluBackward).  dy, pre, dx bf16 [rows, N]
+ * contiguous; colsum fp32 [N], accumulated into (zero it for a plain sum). */
+int dvla_act_bwd_colsum(const void* dy_bf16, const void* pre_bf16, void* dx_bf16, int64_t rows, int64_t N, int32_t act,
+                        float* colsum_f32, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Fused losses: each writes  loss_out[0] += weight * loss  (fp32, device) and dpred = weight * dloss/dpred * gscale.
@@ -253,7 +264,7 @@ int dvla_set_sm_budget(int n_sms);
  * Workspace sizes (bytes) of the ops that need caller-provided scratch -- the library never allocates device memory:
  *   attn_bwd : `delta` fp32 [B, H, Lq]  (rowsum(dO * O), FlashAttention-2 backward)
  *   silog    : `stats` fp32 [2]         (sum d, sum d^2; zeroed by the caller before dvla_silog_stats)
- *   gemm     : 0                        (split-K partial sums are reduced in place with red.global.add)
+ *   gemm     : optional (dvla_gemm_args.workspace): fp32 partial tiles + arrival counters of the K-split tail / split-K
  * ------------------------------------------------------------------------------------------------------------- */
 int64_t dvla_attn_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Lq);
 int64_t dvla_silog_workspace_bytes(void);

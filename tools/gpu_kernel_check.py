@@ -544,8 +544,68 @@ def _check_sumsq_deterministic():
     report("sumsq bit-reproducible", 0.0 if all(torch.equal(outs[0], o) for o in outs) else 1.0, 0.5)
 
 
+def group_act_bwd_colsum():
+    """dx = dy * act'(pre) with the column sums of dx accumulated in the same pass (dvla_act_bwd_colsum)."""
+    g = torch.Generator().manual_seed(11)
+    for (rows, N, act) in [(777, 4096, L.ACT_GELU_ERF), (2600, 3072, L.ACT_GELU_TANH), (33, 264, L.ACT_SILU), (5, 4096, L.ACT_RELU),
+                           (10320, 4096, L.ACT_GELU_TANH), (42400, 4096, L.ACT_GELU_ERF)]:
+        dy = (torch.randn(rows, N, generator=g) * 0.5).to(dev, torch.bfloat16)
+        pre = torch.randn(rows, N, generator=g).to(dev, torch.bfloat16)
+        acc0 = torch.randn(N, generator=g).to(dev)
+        acc = acc0.clone()
+        dx = L.act_bwd(dy, pre, act, colsum_out=acc)
+        x = pre.float().requires_grad_(True)
+        gref = torch.autograd.grad(act_ref(x, act), x, dy.float())[0]
+        report(f"act_bwd_colsum dx {rows}x{N} act{act}", rel(dx, gref), 8e-3)
+        report(f"act_bwd_colsum sum {rows}x{N} act{act}", rel(acc - acc0, gref.sum(0)), 2e-3)
+        plain = L.act_bwd(dy, pre, act)
+        report(f"act_bwd_colsum dx == act_bwd {rows}x{N}", float((dx.float() - plain.float()).abs().max()), 0.0)
+        if rows >= 10000:
+            t_f = bench(lambda: L.act_bwd(dy, pre, act, colsum_out=acc))
+            t_a = bench(lambda: L.act_bwd(dy, pre, act))
+            t_c = bench(lambda: L.colsum_accum(plain, acc))
+            by = rows * N * 6
+            print(f"     fused {t_f*1e3:.1f} us ({by/t_f/1e6:.0f} GB/s)  vs  act_bwd {t_a*1e3:.1f} us + colsum {t_c*1e3:.1f} us", flush=True)
+
+
+def group_gemm_tail():
+    """K-split tail of the persistent GEMMs (partial last wave cut along K, fp32 reduction through the workspace):
+    results against fp32 torch for every epilogue, repeated launches (self-cleaning workspace), timing of the step's shapes."""
+    g = torch.Generator(device="cpu").manual_seed(5)
+    for (M, N, K, b_mn) in [(10320, 1024, 4096, False), (10320, 1024, 4096, True), (10320, 1024, 3072, False),
+                            (10320, 1024, 1024, True), (2580, 1024, 4096, False), (1300, 512, 2048, False),
+                            (5000, 1000, 1536, True), (31520, 768, 3072, False)]:
+        A = (torch.randn(M, K, generator=g) * 0.5).to(dev, torch.bfloat16)
+        W = (torch.randn(N, K, generator=g) * 0.05).to(dev, torch.bfloat16)
+        w = W.t().contiguous() if b_mn else W
+        bias = torch.randn(N, generator=g).to(dev, torch.bfloat16)
+        res = torch.randn(M, N, generator=g).to(dev, torch.bfloat16)
+        ref = A.float() @ W.float().t()
+        out = L.gemm(A, w, b_mn=b_mn)
+        report(f"gemm tail plain M{M} N{N} K{K} b_mn={int(b_mn)}", rel(out, ref), 6e-3)
+        out2 = L.gemm(A, w, b_mn=b_mn)
+        report(f"gemm tail repeat == first M{M} N{N} K{K}", float((out.float() - out2.float()).abs().max()), 0.0079 * float(ref.abs().max()))   # <= 1 bf16 ulp (fp32 atomic order)
+        aux = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        out = L.gemm(A, w, b_mn=b_mn, bias=bias, act=L.ACT_GELU_TANH, residual=res, aux_out=aux)
+        pre = ref + bias.float()
+        report(f"gemm tail bias+gelu+res M{M} N{N} K{K}", rel(out, act_ref(pre, L.ACT_GELU_TANH) + res.float()), 6e-3)
+        report(f"gemm tail aux_out M{M} N{N} K{K}", rel(aux, pre), 6e-3)
+        ws = L.gemm_workspace(A.device)
+        report(f"gemm tail workspace left zero M{M} N{N} K{K}", float(ws.view(torch.int32).abs().max()), 0.0)
+        ms = bench(lambda: L.gemm(A, w, b_mn=b_mn, bias=bias, residual=res))
+        print(f"     M{M} N{N} K{K} b_mn={int(b_mn)} bias+res: {ms*1e3:.1f} us {2*M*N*K/ms/1e9:.0f} TFLOP/s", flush=True)
+    # dropout epilogue: same mask as the stand-alone kernel
+    M, N, K = 10320, 1024, 4096
+    A = (torch.randn(M, K, generator=g) * 0.5).to(dev, torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) * 0.05).to(dev, torch.bfloat16)
+    plain = L.gemm(A, W)
+    dropped = L.gemm(A, W, dropout_p=0.1, dropout_seed=77)
+    want = L.dropout(plain, 0.1, 77)
+    report("gemm tail dropout epilogue == dropout(plain)", rel(dropped, want), 4e-3)
+
+
 GROUPS = {"gemm_basic": group_gemm_basic, "gemm_splitk": group_gemm_splitk, "gemm_big": group_gemm_big, "gemm_epilogue": group_gemm_epilogue,
-          "norm": group_norm, "attn": group_attn, "attn_perf": group_attn_perf, "loss": group_loss}
+          "norm": group_norm, "attn": group_attn, "attn_perf": group_attn_perf, "loss": group_loss, "act_bwd_colsum": group_act_bwd_colsum, "gemm_tail": group_gemm_tail}
 
 if __name__ == "__main__":
     grp = sys.argv[1]

@@ -145,7 +145,7 @@ _gemm_ws = {}
 def gemm_workspace(device):
     """The GEMM scratch (fp32 partial tiles + arrival counters, include/dvla.h `dvla_gemm_args.workspace`) of the CURRENT
     stream of `device`: one zero-initialised buffer per (device, stream), kept for the life of the process -- the kernels
-    leave it all zero again, and calls on one stream are ordered, so they can share it."""
+    leave its counter block zero again, and calls on one stream are ordered, so they can share it."""
     key = (device.index if device.index is not None else torch.cuda.current_device(),
            torch.cuda.current_stream(device).cuda_stream)
     ws = _gemm_ws.get(key)

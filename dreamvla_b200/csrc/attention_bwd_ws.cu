@@ -143,6 +143,7 @@ attn_bwd_dq_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const uint32_t lane_off = (static_cast<uint32_t>(quarter * 32) << 16) + half * 32;
     const float sc = p.scale * B_LOG2E;
     const bool has_drop = p.drop_scale != 0.f;
+    const uint32_t th16 = p.drop_thresh << 16;
     const uint64_t seed = p.drop_seed + ((has_drop && p.drop_seed_ptr) ? __ldg(p.drop_seed_ptr) : 0ull);
     const int nblk = (p.Lk + 7) >> 3;
     const float lse2 = (row < p.Lq) ? p.lse[bh * p.Lq + row] * B_LOG2E : INFINITY;
@@ -185,8 +186,8 @@ attn_bwd_dq_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             for (int i = 0; i < 4; ++i) pk[g * 4 + i] = 0u;
             continue;
           }
-          uint32_t keep = 0xffu;
-          if (has_drop) keep = dropout_keep8(seed, (bh * p.Lq + row) * nblk + (k0 >> 3) + g, p.drop_thresh);
+          uint4 rnd = make_uint4(0, 0, 0, 0);
+          if (has_drop) rnd = philox4x32(seed, (bh * p.Lq + row) * nblk + (k0 >> 3) + g);
           float ds[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -194,7 +195,7 @@ attn_bwd_dq_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             float pv = ex2_approx(fmaf(sv[cc], sc, -lse2));
             if (f == 1) pv = ((wv >> cc) & 1u) ? pv : 0.f;
             float dp = dpv[cc];
-            if (has_drop) dp = ((keep >> i) & 1u) ? dp * p.drop_scale : 0.f;
+            if (has_drop) dp = dropout_keep_elem(rnd, th16, i) ? dp * p.drop_scale : 0.f;
             ds[i] = pv * (dp - dlt);
           }
 #pragma unroll

@@ -232,6 +232,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const float sc = p.scale * WS_LOG2E;
       const long long bh = static_cast<long long>(b) * p.H + h;
       const bool has_drop = p.drop_scale != 0.f;
+      const uint32_t th16 = p.drop_thresh << 16;
       const uint64_t seed = p.drop_seed + ((has_drop && p.drop_seed_ptr) ? __ldg(p.drop_seed_ptr) : 0ull);
       const int nblk = (p.Lk + 7) >> 3;
       const uint32_t* mrow = p.mask ? p.mask + static_cast<long long>(row < p.Lq ? row : 0) * p.mask_words : nullptr;
@@ -318,10 +319,10 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               e[i] = ex2_approx(fmaf(s[g * 8 + i], sc, -m_use));   // masked (-inf) -> 0
               lsum += e[i];
             }
-            if (has_drop) {
-              const uint32_t keep = dropout_keep8(seed, blk0 + g, p.drop_thresh);
+            if (has_drop) {                 // dropped probabilities -> 0; the 1/(1-p) factor is applied once, to O (finalize)
+              const uint4 rnd = philox4x32(seed, blk0 + g);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) e[i] = ((keep >> i) & 1u) ? e[i] * p.drop_scale : 0.f;
+              for (int i = 0; i < 8; ++i) e[i] = dropout_keep_elem(rnd, th16, i) ? e[i] : 0.f;
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) pk[g * 4 + i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
@@ -368,7 +369,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       if (quarter == 2 && lane == 0) trace(64 + t * 64 + 60);
       if (warp_active) {
-        const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+        const float inv = l_run > 0.f ? (has_drop ? p.drop_scale : 1.0f) / l_run : 0.f;
         bf16* dst = p.out + b * p.o_sb + static_cast<long long>(row) * p.o_ss + h * p.o_sh;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {

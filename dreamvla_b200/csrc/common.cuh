@@ -390,5 +390,12 @@ __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t blk, u
   m |= ((r.w & 0xFFFFu) >= thresh) << 6; m |= ((r.w >> 16) >= thresh) << 7;
   return m;
 }
+// The same mask without materialising it: element j of the block whose Philox words are `r` is kept iff its 16-bit draw
+// (low half of word j/2 for even j, high half for odd j) >= thresh.  `th16` = thresh << 16, so the high half compares as
+// the whole word and the low half after one shift: 1-2 instructions per element instead of ~6 to build and test mask bits.
+__device__ __forceinline__ bool dropout_keep_elem(const uint4& r, uint32_t th16, int j) {
+  const uint32_t w = j < 2 ? r.x : j < 4 ? r.y : j < 6 ? r.z : r.w;
+  return (j & 1) ? (w >= th16) : ((w << 16) >= th16);
+}
 
 }  // namespace dvla

@@ -39,8 +39,8 @@ struct GemmParams {
   // K-split TAIL (see map_unit): tiles [tail_first, total) are each cut into tail_splits k-ranges of tail_kbps k-blocks; the
   // partial accumulators meet in an fp32 workspace and the LAST unit to arrive runs the normal epilogue on the full sum
   int tail_first, tail_splits, tail_kbps;
-  float* tail_ws;               // [slot][16 warp regions][BN/4 columns][32 lanes] fp32, all zero between launches
-  unsigned* tail_cnt;           // [slot][16] arrival counters, all zero between launches
+  float* tail_ws;               // [CTA slot][16 warp regions][split][BN/16][32 lanes][4] fp32 partial accumulators
+  unsigned* tail_cnt;           // [CTA slot][16] arrival counters, all zero between launches
   float alpha;
   float drop_scale;        // 1/(1-p_eff), 0 => dropout disabled
   uint32_t drop_thresh;    // round(p*65536)
@@ -338,18 +338,20 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_acc /* tmem base + acc*
 // (p.tail_splits > 1): units [0, tail_first) are whole tiles -- a whole number of waves -- and the tiles that would form
 // the last, partly filled wave are cut along K so that every CTA (pair) gets ~1/tail_splits of a tile instead of a
 // few getting a whole one while the rest idle:  2.2 waves of tiles cost 2.2 tile-times instead of 3.
-struct Unit { int tile, kb0, kb1, slot; };   // slot < 0: whole tile / atomic split-K; >= 0: tail tile index
+struct Unit { int tile, kb0, kb1, slot, split; };   // slot < 0: whole tile / atomic split-K; >= 0: tail tile index
 __device__ __forceinline__ int gemm_total_units(int total_tiles, const GemmParams& p) {
   return p.tail_splits > 1 ? p.tail_first + (total_tiles - p.tail_first) * p.tail_splits : total_tiles * p.k_splits;
 }
 __device__ __forceinline__ Unit map_unit(int unit, int total_tiles, const GemmParams& p) {
   Unit u;
   if (p.tail_splits > 1) {
+    u.split = 0;
     if (unit < p.tail_first) { u.tile = unit; u.kb0 = 0; u.kb1 = p.num_k_blocks; u.slot = -1; return u; }
     const int t = unit - p.tail_first, nt = total_tiles - p.tail_first;
     u.slot = t % nt;
     u.tile = p.tail_first + u.slot;
-    u.kb0 = (t / nt) * p.tail_kbps;
+    u.split = t / nt;
+    u.kb0 = u.split * p.tail_kbps;
     u.kb1 = min(p.num_k_blocks, u.kb0 + p.tail_kbps);
     return u;
   }
@@ -357,27 +359,32 @@ __device__ __forceinline__ Unit map_unit(int unit, int total_tiles, const GemmPa
   u.kb0 = (unit / total_tiles) * p.kb_per_split;
   u.kb1 = min(p.num_k_blocks, u.kb0 + p.kb_per_split);
   u.slot = -1;
+  u.split = 0;
   return u;
 }
 
 // Epilogue of one K-split tail unit for one epilogue warp.  The warp owns the same 32-row x BN/4-column region of the
-// tile in every split, so the reduction is per warp region, with no CTA-wide synchronisation:
-//   1. TMEM -> registers -> red.global.add.f32 into the region's workspace ([column][lane]: 128 contiguous bytes per warp
-//      instruction); the accumulator stage is handed back to the MMA warp as soon as it has been read;
+// tile in every split, so the reduction is per warp region, with no CTA-wide synchronisation and no atomics on data:
+//   1. TMEM -> registers -> this split's fp32 slice of the workspace, 16 bytes per lane per store ([col/4][lane][4]: a warp
+//      instruction writes 512 contiguous bytes); the accumulator stage is handed back to the MMA warp once it is read;
 //   2. __threadfence, one atomicAdd on the region's arrival counter;
-//   3. the warp that arrives LAST reads the complete fp32 sum back (L2, ld.cg), zeroes workspace and counter for the
-//      next launch, and runs the ordinary fused epilogue (bias / act / dropout / residual / aux) on it -- one rounding to
-//      bf16, whatever the number of splits.
+//   3. the warp that arrives LAST sums the slices of all splits in split order (L2 reads, ld.cg) -- a fixed order, so the
+//      result does not depend on which split finished last -- resets the counter, and runs the ordinary fused epilogue
+//      (bias / act / dropout / residual / aux) on the sum: one rounding to bf16 whatever the number of splits.
+// (fp32 red.global.add into one shared slice was measured first: ~20 us per GEMM for 17 MB of partials, the L2 atomic
+//  units retire about one 4-byte element per clock per slice; plain vector stores + one read pass cost a third of that.)
 template <int BN, typename ArriveFn>
 __device__ __forceinline__ void epilogue_tile_tail(uint32_t t_acc, uint8_t* staging, int warp, int lane, int m0, int n0,
-                                                   const GemmParams& p, int cta_slot, ArriveFn arrive_tmem_free) {
+                                                   const GemmParams& p, int cta_slot, int split, ArriveFn arrive_tmem_free) {
   const int q = warp & 3;
   const int quarter = (warp - 2) >> 2;
   const uint32_t t_lane = t_acc + (static_cast<uint32_t>(q * 32) << 16);
   uint8_t* stage = staging + (warp - 2) * EPI_STAGE_BYTES;
   constexpr int CPW = BN / 4 / 32;
+  constexpr int REGION = (BN / 4) * 32;                     // floats per warp region
   const long long region = static_cast<long long>(cta_slot) * NUM_EPI_WARPS + (warp - 2);
-  float* ws = p.tail_ws + region * (BN / 4) * 32 + lane;
+  float* base = p.tail_ws + region * p.tail_splits * REGION + lane * 4;     // + split * REGION + (col / 4) * 128
+  float* mine = base + static_cast<long long>(split) * REGION;
 #pragma unroll 1
   for (int ci = 0; ci < CPW; ++ci) {
     uint32_t r[32];
@@ -389,8 +396,10 @@ __device__ __forceinline__ void epilogue_tile_tail(uint32_t t_acc, uint8_t* stag
       if (lane == 0) arrive_tmem_free();
     }
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      asm volatile("red.global.add.f32 [%0], %1;" :: "l"(ws + (ci * 32 + j) * 32), "f"(__uint_as_float(r[j])) : "memory");
+    for (int j = 0; j < 8; ++j)
+      __stcg(reinterpret_cast<float4*>(mine + (ci * 8 + j) * 128),
+             make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                         __uint_as_float(r[4 * j + 3])));
   }
   __threadfence();
   __syncwarp();
@@ -403,13 +412,19 @@ __device__ __forceinline__ void epilogue_tile_tail(uint32_t t_acc, uint8_t* stag
 #pragma unroll 1
   for (int ci = 0; ci < CPW; ++ci) {
     const int c = quarter * (BN / 4) + ci * 32;
+    if (n0 + c >= p.N) continue;     // warp-uniform
     float v[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      v[j] = __ldcg(ws + (ci * 32 + j) * 32);
-      __stcg(ws + (ci * 32 + j) * 32, 0.f);
+    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+#pragma unroll 1
+    for (int sp = 0; sp < p.tail_splits; ++sp) {
+      const float* src = base + static_cast<long long>(sp) * REGION + ci * 8 * 128;
+      float4 t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = __ldcg(reinterpret_cast<const float4*>(src + j * 128));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { v[4 * j] += t[j].x; v[4 * j + 1] += t[j].y; v[4 * j + 2] += t[j].z; v[4 * j + 3] += t[j].w; }
     }
-    if (n0 + c >= p.N) continue;     // warp-uniform
     epilogue_chunk_staged(v, stage, lane, m0 + q * 32, n0 + c, p);
   }
 }
@@ -533,7 +548,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_after();
       uint64_t* free_bar = &tempty_bar[acc];
       if (u.slot >= 0)
-        epilogue_tile_tail<BN>(tmem_base + acc * BN, staging, warp, lane, m0, n0, p, u.slot, [free_bar] { mbar_arrive(free_bar); });
+        epilogue_tile_tail<BN>(tmem_base + acc * BN, staging, warp, lane, m0, n0, p, u.slot, u.split, [free_bar] { mbar_arrive(free_bar); });
       else
         epilogue_tile<BN>(tmem_base + acc * BN, staging, warp, lane, m0, n0, p, [free_bar] { mbar_arrive(free_bar); });
       acc ^= 1;
@@ -691,7 +706,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       tc_fence_after();
       uint64_t* free_bar = &tempty_bar[acc];
       if (u.slot >= 0)
-        epilogue_tile_tail<BN>(tmem_base + acc * BN, staging, warp, lane, m0, n0, p, 2 * u.slot + static_cast<int>(rank),
+        epilogue_tile_tail<BN>(tmem_base + acc * BN, staging, warp, lane, m0, n0, p, 2 * u.slot + static_cast<int>(rank), u.split,
                                [free_bar] { mbar_arrive_leader(free_bar); });
       else
         epilogue_tile<BN>(tmem_base + acc * BN, staging, warp, lane, m0, n0, p, [free_bar] { mbar_arrive_leader(free_bar); });
@@ -916,20 +931,29 @@ static bool splitk_enabled() {
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-// DVLA_GEMM_TAIL=0 disables the K-split tail / fp32 split-K reduction (every unit is then a whole tile or an atomic split)
+// DVLA_GEMM_TAIL=0 disables the K-split tail (every unit of a plain GEMM is then a whole tile)
 static bool tail_enabled() {
   static const bool on = [] { const char* e = getenv("DVLA_GEMM_TAIL"); return !(e && !strcmp(e, "0")); }();
   return on;
 }
-// workspace = [16384 arrival counters (64 KB)] [fp32 partial tiles: 128 x BN x 4 bytes per CTA slot]
+// split-K weight gradients: partial sums added with red.global.add.bf16x2 (default), or with DVLA_GEMM_SPLITK=fp32 the same
+// fp32 slices + ordered fix-up as the tail: one bf16 rounding per accumulation (rel-L2 vs fp32 1.66e-3 instead of
+// 2.7e-3 - 4.3e-3) and a reproducible summation order, for +5 % ... +49 % per weight-gradient GEMM (the last unit's read-back
+// of the other splits' slices is exposed at the end of the kernel) = +1.4 ms per C2 step (profiles/r2_notes.md)
+static bool splitk_fp32() {
+  static const bool on = [] { const char* e = getenv("DVLA_GEMM_SPLITK"); return e && !strcmp(e, "fp32"); }();
+  return on;
+}
+// workspace = [16384 arrival counters (64 KB), zero between launches] [fp32 partial tiles: 128 x BN x 4 bytes per CTA and split]
 constexpr int64_t TAIL_CNT_BYTES = 65536;
-constexpr int64_t TAIL_WS_SLOTS = 160;               // 128 x 256 fp32 slots: covers every partial wave of 148 CTAs / 74 pairs
-int64_t gemm_workspace_bytes() { return TAIL_CNT_BYTES + TAIL_WS_SLOTS * 128 * 256 * 4; }
+constexpr int64_t TAIL_WS_SLICES = 512;              // 128 x 256 fp32 slices (64 MB): a split tail wave of 74 CTA pairs needs
+                                                     // <= 148, a 4096 x 1024 weight gradient split in two 256
+int64_t gemm_workspace_bytes() { return TAIL_CNT_BYTES + TAIL_WS_SLICES * 128 * 256 * 4; }
 
-static bool tail_fits(const dvla_gemm_args* a, long long tail_tiles, int ctas_per_tile, int bn) {
+static bool tail_fits(const dvla_gemm_args* a, long long tail_tiles, int ctas_per_tile, int bn, int splits) {
   if (!a->workspace || (reinterpret_cast<uintptr_t>(a->workspace) & 15)) return false;
   const long long slots = tail_tiles * ctas_per_tile;
-  return slots * NUM_EPI_WARPS * 4 <= TAIL_CNT_BYTES && TAIL_CNT_BYTES + slots * 128LL * bn * 4 <= a->workspace_bytes;
+  return slots * NUM_EPI_WARPS * 4 <= TAIL_CNT_BYTES && TAIL_CNT_BYTES + slots * splits * 128LL * bn * 4 <= a->workspace_bytes;
 }
 static void set_tail(GemmParams& p, const dvla_gemm_args* a, int first, int splits, int kbps) {
   p.tail_first = first; p.tail_splits = splits; p.tail_kbps = kbps;
@@ -950,11 +974,11 @@ static void plan_tail(GemmParams& p, const dvla_gemm_args* a, long long total_ti
   const int kbps = (p.num_k_blocks + tsp - 1) / tsp;
   tsp = (p.num_k_blocks + kbps - 1) / kbps;
   if (tsp < 2) return;
-  const float c0 = 8.f, c_fix = 12.f;
+  const float c0 = 8.f, c_fix = 20.f;    // ~8 us of slice writes + read-back vs 0.43 us per k-block of a 256 x 256 tile
   const float now = (float)(full_waves + 1) * ((float)p.num_k_blocks + c0);
   const float with_tail = (float)full_waves * ((float)p.num_k_blocks + c0) + (float)kbps + c0 + c_fix;
   if (with_tail > 0.93f * now) return;
-  if (!tail_fits(a, rem, ctas_per_tile, bn)) return;
+  if (!tail_fits(a, rem, ctas_per_tile, bn, tsp)) return;
   set_tail(p, a, (int)(full_waves * slots), tsp, kbps);
 }
 
@@ -1034,9 +1058,9 @@ int gemm_dispatch(const dvla_gemm_args* a, cudaStream_t stream) {
     if (best_s > 1) {
       const int kbps = (p.num_k_blocks + best_s - 1) / best_s;
       const int bn_sel = best_cfg == 2 ? 128 : 256;
-      if (tail_enabled() && tail_fits(a, tl[best_cfg], best_cfg == 0 ? 2 : 1, bn_sel)) {
-        // every tile is split; the partial sums meet in fp32 and the last unit adds the complete product to the gradient
-        // (out = residual = G): ONE bf16 rounding per accumulation instead of one per split
+      if (splitk_fp32() && tail_fits(a, tl[best_cfg], best_cfg == 0 ? 2 : 1, bn_sel, best_s)) {
+        // every tile is split; the partial sums meet in fp32 slices and the last unit adds the complete product to the
+        // gradient (out = residual = G): ONE bf16 rounding per accumulation instead of one per split, fixed summation order
         set_tail(p, a, 0, best_s, kbps);
       } else {
         p.k_splits = best_s;

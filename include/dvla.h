@@ -64,10 +64,11 @@ typedef struct {
   float dropout_p;        /* 0 disables */
   uint64_t dropout_seed;  /* RNG block = m*ceil(N/8) + n/8, bit n%8 (same convention as dvla_dropout) */
   const uint64_t* dropout_seed_ptr; /* optional DEVICE counter added to dropout_seed at run time (CUDA-graph replays) */
-  /* optional scratch of >= dvla_gemm_workspace_bytes() bytes, 16-byte aligned, ALL ZERO before the first call and owned by
-   * one stream (calls on one stream may share it; every call leaves it all zero again).  With it, the output tiles that
-   * would form a partly filled last wave are cut along K and reduced in fp32 through this buffer, and split-K weight
-   * gradients are reduced in fp32 instead of with bf16 atomics.  NULL: whole tiles / bf16 red.global.add only. */
+  /* optional scratch of >= dvla_gemm_workspace_bytes() bytes, 16-byte aligned, owned by one stream (calls on one stream may
+   * share it).  Its first 64 KB are arrival counters: ZERO before the first call, left zero by every call; the rest holds
+   * fp32 partial tiles and needs no initialisation.  With it, the output tiles that would form a partly filled last wave
+   * are cut along K and summed in fp32 (fixed order) by the last unit to arrive, and split-K weight gradients are reduced
+   * the same way instead of with bf16 atomics.  NULL: whole tiles / bf16 red.global.add only. */
   void* workspace;
   int64_t workspace_bytes;
 } dvla_gemm_args;

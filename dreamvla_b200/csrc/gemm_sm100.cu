@@ -966,7 +966,10 @@ static void plan_tail(GemmParams& p, const dvla_gemm_args* a, long long total_ti
   if (!tail_enabled() || !p.staged_ok || p.k_splits != 1 || total_tiles <= 0) return;
   const long long full_waves = total_tiles / slots;
   const long long rem = total_tiles - full_waves * slots;
-  if (rem == 0) return;
+  // Only GEMMs of at least one full wave: a row's result then depends on M only for the large training GEMMs.  Below one
+  // wave (every GEMM of action inference) each output row is computed in the same K order whatever the batch it is in --
+  // the incremental rollout's "bit-identical to the full window" property (tests/test_rollout_gpu.py) rests on that.
+  if (rem == 0 || full_waves == 0) return;
   int tsp = (int)(slots / rem);
   if (tsp > 8) tsp = 8;
   if (tsp > p.num_k_blocks / 4) tsp = p.num_k_blocks / 4;

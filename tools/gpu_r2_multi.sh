@@ -20,9 +20,10 @@ for l in sys.stdin:
 run default DVLA_X=1
 run nobudget DVLA_SM_BUDGET=0
 if [ "$N" != "2" ]; then
-  run ctas8 DVLA_NCCL_CTAS=8
-  run ctas32 DVLA_NCCL_CTAS=32
   run nooverlap DVLA_AR_OVERLAP=0
+  [ -n "$MORE" ] && run ctas8 DVLA_NCCL_CTAS=8
+  [ -n "$MORE" ] && run ctas32 DVLA_NCCL_CTAS=32
+  timeout 300 $TR --master-port 29560 tools/ddp_timeline.py 2>&1 | grep -E "^\[timeline\]|Error|Traceback" | cut -c1-220 | tee gpurun_out/r2_ddp_timeline_${N}gpu.log
 fi
 port=$((port+1)); t0=$(date +%s)
 timeout 300 $TR --master-port $port bench.py --impl reference_gpu --gpus $N --steps 5 --warmup 3 --batch 8 > gpurun_out/r2_bench_${N}gpu_reference_gpu.log 2>&1

@@ -319,16 +319,19 @@ def run_ours(args):
                "input_pipeline": "train_utils.prefetch_to_device (copy stream, 2 persistent device slots)",
                "clocks": sampler2.summary() if sampler2 else None}
 
-        if os.environ.get("DVLA_E2E_PROBE") and rank == 0 and world == 1:
+        if os.environ.get("DVLA_E2E_PROBE"):
             # diagnostic (stderr only): which part of the input pipeline costs device time when it runs beside the step
             def timed(fn):
                 fn(3)
-                torch.cuda.synchronize()
+                sync_all()
                 e0.record()
                 fn(args.steps)
                 e1.record()
-                torch.cuda.synchronize()
-                return e0.elapsed_time(e1) / args.steps
+                sync_all()
+                tt = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+                if world > 1:
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                return float(tt)
             dbf = {k: torch.empty(v.shape, dtype=(torch.bfloat16 if v.is_floating_point() else v.dtype), device=dev) for k, v in host.items()}
             dst = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
 
@@ -359,10 +362,20 @@ def run_ours(args):
             def prefetch3(n):
                 for dbatch in prefetch_to_device(host_batches(n), dev, slots=3):
                     step(dbatch)
-            for name, fn in (("resident", resident), ("resident+copy_in", resident_copy_in), ("dma_beside", dma_beside),
-                             ("dma+cast_beside", dma_cast_beside), ("prefetch(2)", e2e_run), ("prefetch(3)", prefetch3),
-                             ("resident", resident)):
-                print(f"[e2e probe] {name:18s} {timed(fn):8.3f} ms/step", file=sys.stderr, flush=True)
+            def resident_d2h(n):          # + the loss read-back of every step
+                for _ in range(n):
+                    ls = step(batch)
+                    loss_host.copy_(ls.reshape(1).float(), non_blocking=True)
+
+            def prefetch_no_d2h(n):
+                for dbatch in prefetch_to_device(host_batches(n), dev):
+                    step(dbatch)
+            for name, fn in (("resident", resident), ("resident+d2h_loss", resident_d2h), ("resident+copy_in", resident_copy_in),
+                             ("dma_beside", dma_beside), ("dma+cast_beside", dma_cast_beside), ("prefetch(2) no d2h", prefetch_no_d2h),
+                             ("prefetch(2)", e2e_run), ("prefetch(3)", prefetch3), ("resident", resident)):
+                tms = timed(fn)
+                if rank == 0:
+                    print(f"[e2e probe] world={world} {name:18s} {tms:8.3f} ms/step", file=sys.stderr, flush=True)
 
     stage("e2e done")
     # ---- roofline of the dominant kernel (tcgen05 GEMM) ----------------------------------------------------------------

@@ -682,9 +682,9 @@ class _DeviceSlot:
 
 
 def prefetch_to_device(loader, device, to_host_dict=None, dtype=torch.bfloat16, slots=2):
-    """Iterate `loader`, yielding each batch as a dict of DEVICE tensors one batch AHEAD of the consumer: the host->device
-    copies of batch i+1 run on a copy stream while batch i is being consumed on the current stream, so a step's input transfer
-    (193 MB at C2, ~3.5 ms over PCIe 5 x16) hides behind the previous step's kernels.
+    """Iterate `loader`, yielding each batch as a dict of DEVICE tensors; the host->device copies of batch i+1 are enqueued on a
+    copy stream right after the consumer has enqueued step i, so a step's input transfer (193 MB at C2, ~3.5 ms over PCIe 5
+    x16) runs beside that step's kernels.  The host stays at most one step ahead of the device (see `stage`).
 
     `to_host_dict(item)` maps a loader item to a dict of host tensors (default: the item itself); pinned host memory is
     needed for the copy to be asynchronous.  The device buffers are `slots` persistent sets reused round-robin (no allocator
@@ -707,9 +707,13 @@ def prefetch_to_device(loader, device, to_host_dict=None, dtype=torch.bfloat16, 
         except StopIteration:
             return None
         slot = ring[i % len(ring)]
+        if slot.consumed is not None:
+            # HOST-side wait for the step that read this slot's buffers (it finished long ago unless the host runs more than a
+            # step ahead).  A device-side wait (copy_stream.wait_event) would park the copy in the stream's hardware queue
+            # until the event fires; with the overlapped NCCL all-reduces of the data-parallel step in flight, copies parked
+            # or released at arbitrary points of the step cost 8-26 ms per step at 4-8 GPUs (profiles/r2_multi_gpu.md)
+            slot.consumed.synchronize()
         with torch.cuda.stream(copy_stream):
-            if slot.consumed is not None:
-                copy_stream.wait_event(slot.consumed)      # the step that read this slot's buffers has finished
             dev = slot.fill(to_host_dict(item), device, dtype)
             ready = torch.cuda.Event()
             ready.record(copy_stream)
@@ -717,17 +721,16 @@ def prefetch_to_device(loader, device, to_host_dict=None, dtype=torch.bfloat16, 
 
     i = 0
     nxt = stage(i)
-    prev_slot = None
     while nxt is not None:
         dev, ready, slot = nxt
         cur = torch.cuda.current_stream(device)
-        if prev_slot is not None:                          # everything enqueued so far includes the consumer of the previous batch
-            prev_slot.consumed = cur.record_event()
         cur.wait_event(ready)
+        yield dev                                          # the consumer enqueues step i on `cur`
+        cur = torch.cuda.current_stream(device)
+        slot.consumed = torch.cuda.Event(blocking=True)    # blocking: the host thread sleeps in synchronize() instead of spinning
+        slot.consumed.record(cur)
         i += 1
-        nxt = stage(i)                                     # batch i+1 starts moving before batch i is handed out
-        prev_slot = slot
-        yield dev
+        nxt = stage(i)                                     # batch i+1 moves while step i runs
 
 
 def train_one_epoch_calvin(args, model, epoch, calvin_loader, optimizer, lr_scheduler, device_id, wandb):

@@ -6,6 +6,7 @@ PyTorch is used for device memory and streams only (tensor.data_ptr(), torch.cud
 from __future__ import annotations
 
 import ctypes as C
+import threading
 import os
 
 import torch
@@ -140,6 +141,7 @@ def _need_cuda(*ts) -> None:
 # raw op wrappers (no autograd)
 # ----------------------------------------------------------------------------------------------------------------------
 _gemm_ws = {}
+_gemm_ws_lock = threading.Lock()
 
 
 def gemm_workspace(device):
@@ -150,7 +152,10 @@ def gemm_workspace(device):
            torch.cuda.current_stream(device).cuda_stream)
     ws = _gemm_ws.get(key)
     if ws is None:
-        ws = _gemm_ws[key] = torch.zeros(int(load().dvla_gemm_workspace_bytes(None)), device=device, dtype=torch.uint8)
+        with _gemm_ws_lock:                 # forward thread and autograd's backward thread may both arrive here first
+            ws = _gemm_ws.get(key)
+            if ws is None:
+                ws = _gemm_ws[key] = torch.zeros(int(load().dvla_gemm_workspace_bytes(None)), device=device, dtype=torch.uint8)
     return ws
 
 

@@ -29,6 +29,11 @@ class GemmArgs(C.Structure):
                 ("workspace", _vp), ("workspace_bytes", _i64)]
 
 
+class GemmPlanInfo(C.Structure):
+    _fields_ = [(n, _i32) for n in ("kernel", "tile_m", "tile_n", "m_tiles", "n_tiles", "k_blocks", "k_splits", "kb_per_split",
+                                    "atomic_out", "tail_first", "tail_splits", "tail_kbps", "units", "grid_ctas")]
+
+
 class LayerNormFwdArgs(C.Structure):
     _fields_ = [("x", _vp), ("gamma", _vp), ("beta", _vp), ("y", _vp), ("mean", _vp), ("rstd", _vp), ("rows", _i64),
                 ("D", _i64), ("ldx", _i64), ("ldy", _i64), ("eps", _f32)]
@@ -82,7 +87,7 @@ class DitSamplerArgs(C.Structure):
 
 
 EXPORTS = [
-    "dvla_version", "dvla_last_error", "dvla_launch_count", "dvla_gemm", "dvla_layernorm_fwd", "dvla_layernorm_bwd",
+    "dvla_version", "dvla_last_error", "dvla_launch_count", "dvla_gemm", "dvla_gemm_plan", "dvla_gemm_plan_unit", "dvla_layernorm_fwd", "dvla_layernorm_bwd",
     "dvla_attn_fwd", "dvla_attn_bwd", "dvla_attn_mask_tiles", "dvla_colsum_accum", "dvla_accum_fp32_into_bf16",
     "dvla_dropout", "dvla_act_bwd", "dvla_act_bwd_colsum", "dvla_cat_broadcast", "dvla_mse_loss", "dvla_cosine_loss", "dvla_silog_stats", "dvla_silog_finish",
     "dvla_sumsq", "dvla_adamw", "dvla_grad_clip_scale", "dvla_attn_bwd_workspace_bytes", "dvla_silog_workspace_bytes",

@@ -36,6 +36,8 @@ int num_sms() {
 
 int gemm_dispatch(const dvla_gemm_args* a, cudaStream_t stream);
 int64_t gemm_workspace_bytes();
+int gemm_plan(const dvla_gemm_args* a, dvla_gemm_plan_info* out);
+int gemm_plan_unit(const dvla_gemm_plan_info* plan, int unit, int* tile, int* kb0, int* kb1, int* slot, int* split);
 int layernorm_fwd_dispatch(const dvla_layernorm_fwd_args* a, cudaStream_t stream);
 int layernorm_bwd_dispatch(const dvla_layernorm_bwd_args* a, cudaStream_t stream);
 int attn_fwd_dispatch(const dvla_attn_fwd_args* a, cudaStream_t stream);
@@ -74,6 +76,11 @@ const char* dvla_last_error(void) { return g_err; }
 int64_t dvla_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int dvla_gemm(const dvla_gemm_args* args, void* stream) { return gemm_dispatch(args, S(stream)); }
+int dvla_gemm_plan(const dvla_gemm_args* args, dvla_gemm_plan_info* out) { return gemm_plan(args, out); }
+int dvla_gemm_plan_unit(const dvla_gemm_plan_info* plan, int32_t unit, int32_t* tile, int32_t* kb0, int32_t* kb1,
+                        int32_t* tail_slot, int32_t* split) {
+  return gemm_plan_unit(plan, unit, tile, kb0, kb1, tail_slot, split);
+}
 int dvla_layernorm_fwd(const dvla_layernorm_fwd_args* a, void* stream) { return layernorm_fwd_dispatch(a, S(stream)); }
 int dvla_layernorm_bwd(const dvla_layernorm_bwd_args* a, void* stream) { return layernorm_bwd_dispatch(a, S(stream)); }
 int dvla_attn_fwd(const dvla_attn_fwd_args* a, void* stream) { return attn_fwd_dispatch(a, S(stream)); }

@@ -339,10 +339,10 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_acc /* tmem base + acc*
 // the last, partly filled wave are cut along K so that every CTA (pair) gets ~1/tail_splits of a tile instead of a
 // few getting a whole one while the rest idle:  2.2 waves of tiles cost 2.2 tile-times instead of 3.
 struct Unit { int tile, kb0, kb1, slot, split; };   // slot < 0: whole tile / atomic split-K; >= 0: tail tile index
-__device__ __forceinline__ int gemm_total_units(int total_tiles, const GemmParams& p) {
+__host__ __device__ __forceinline__ int gemm_total_units(int total_tiles, const GemmParams& p) {
   return p.tail_splits > 1 ? p.tail_first + (total_tiles - p.tail_first) * p.tail_splits : total_tiles * p.k_splits;
 }
-__device__ __forceinline__ Unit map_unit(int unit, int total_tiles, const GemmParams& p) {
+__host__ __device__ __forceinline__ Unit map_unit(int unit, int total_tiles, const GemmParams& p) {
   Unit u;
   if (p.tail_splits > 1) {
     u.split = 0;
@@ -352,12 +352,12 @@ __device__ __forceinline__ Unit map_unit(int unit, int total_tiles, const GemmPa
     u.tile = p.tail_first + u.slot;
     u.split = t / nt;
     u.kb0 = u.split * p.tail_kbps;
-    u.kb1 = min(p.num_k_blocks, u.kb0 + p.tail_kbps);
+    u.kb1 = u.kb0 + p.tail_kbps < p.num_k_blocks ? u.kb0 + p.tail_kbps : p.num_k_blocks;
     return u;
   }
   u.tile = unit % total_tiles;
   u.kb0 = (unit / total_tiles) * p.kb_per_split;
-  u.kb1 = min(p.num_k_blocks, u.kb0 + p.kb_per_split);
+  u.kb1 = u.kb0 + p.kb_per_split < p.num_k_blocks ? u.kb0 + p.kb_per_split : p.num_k_blocks;
   u.slot = -1;
   u.split = 0;
   return u;
@@ -786,6 +786,19 @@ void set_error(const char* fmt, ...);
 void count_launch();
 int num_sms();
 
+// dvla_gemm_plan: the dispatcher runs as usual up to the point where it would encode tensor maps and launch; with this
+// thread-local set it records its decisions instead (host only -- no CUDA call, usable without a GPU)
+static thread_local dvla_gemm_plan_info* g_plan = nullptr;
+static void record_plan(const GemmParams& p, int kernel, int tile_m, int tile_n, int m_tiles, int grid_ctas) {
+  dvla_gemm_plan_info& o = *g_plan;
+  o.kernel = kernel; o.tile_m = tile_m; o.tile_n = tile_n;
+  o.m_tiles = m_tiles; o.n_tiles = p.num_n_tiles; o.k_blocks = p.num_k_blocks;
+  o.k_splits = p.k_splits; o.kb_per_split = p.kb_per_split; o.atomic_out = p.atomic_out;
+  o.tail_first = p.tail_first; o.tail_splits = p.tail_splits; o.tail_kbps = p.tail_kbps;
+  o.units = kernel >= 2 ? gemm_total_units(m_tiles * p.num_n_tiles, p) : 0;
+  o.grid_ctas = grid_ctas;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -868,6 +881,11 @@ static bool set_smem_attr_once(std::once_flag& once, cudaError_t& err, K kern, i
 template <int BN, bool A_MN, bool B_MN>
 static int launch_tc(const dvla_gemm_args* a, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
+  if (g_plan) {
+    const int units = gemm_total_units(p.num_m_tiles * p.num_n_tiles, p);
+    record_plan(p, 2, BM, BN, p.num_m_tiles, units < num_sms() ? units : num_sms());
+    return DVLA_OK;
+  }
   CUtensorMap tmA, tmB;
   if (!A_MN) { if (!make_tmap_2d_bf16(&tmA, a->a, a->K, a->M, a->lda, BK, BM)) return DVLA_ERR_CUDA; }
   else       { if (!make_tmap_2d_bf16(&tmA, a->a, a->M, a->K, a->lda, 64, BK)) return DVLA_ERR_CUDA; }
@@ -892,6 +910,12 @@ static int launch_tc(const dvla_gemm_args* a, const GemmParams& p, cudaStream_t 
 template <bool A_MN, bool B_MN>
 static int launch_tc2(const dvla_gemm_args* a, const GemmParams& p, cudaStream_t stream) {
   using Cfg = Gemm2Cfg;
+  if (g_plan) {
+    const int m2 = (p.M + 2 * BM - 1) / (2 * BM);
+    const int units = gemm_total_units(m2 * p.num_n_tiles, p);
+    record_plan(p, 3, 2 * BM, 256, m2, 2 * (units < num_sms() / 2 ? units : num_sms() / 2));
+    return DVLA_OK;
+  }
   CUtensorMap tmA, tmB;
   if (!A_MN) { if (!make_tmap_2d_bf16(&tmA, a->a, a->K, a->M, a->lda, BK, BM)) return DVLA_ERR_CUDA; }
   else       { if (!make_tmap_2d_bf16(&tmA, a->a, a->M, a->K, a->lda, 64, BK)) return DVLA_ERR_CUDA; }
@@ -1017,6 +1041,11 @@ int gemm_dispatch(const dvla_gemm_args* a, cudaStream_t stream) {
   if (!tma_ok) {
     const long long groups = (long long)p.M * ((p.N + 7) / 8);
     const int threads = 128;
+    if (g_plan) {
+      const bool warp_kernel = p.K >= 128 && groups <= 65536;
+      record_plan(p, warp_kernel ? 1 : 0, 1, 8, p.M, (int)(((warp_kernel ? groups * 32 : groups) + threads - 1) / threads));
+      return DVLA_OK;
+    }
     if (p.K >= 128 && groups <= 65536) {      // long contraction, small output: one warp per output group
       const long long blocks = (groups * 32 + threads - 1) / threads;
       gemm_simt_warp_kernel<<<(unsigned)blocks, threads, 0, stream>>>((const bf16*)a->a, (const bf16*)a->b, a->lda, a->ldb,
@@ -1134,6 +1163,29 @@ int gemm_dispatch(const dvla_gemm_args* a, cudaStream_t stream) {
     case 6: return launch_tc<256, true, false>(a, p, stream);
     default: return launch_tc<256, true, true>(a, p, stream);
   }
+}
+
+int gemm_plan(const dvla_gemm_args* a, dvla_gemm_plan_info* out) {
+  if (!out) { set_error("dvla_gemm_plan: null output"); return DVLA_ERR_INVALID; }
+  memset(out, 0, sizeof(*out));
+  g_plan = out;
+  const int rc = gemm_dispatch(a, nullptr);
+  g_plan = nullptr;
+  return rc;
+}
+int gemm_plan_unit(const dvla_gemm_plan_info* plan, int unit, int* tile, int* kb0, int* kb1, int* slot, int* split) {
+  if (!plan || plan->kernel < 2 || unit < 0 || unit >= plan->units) { set_error("dvla_gemm_plan_unit: bad plan / unit"); return DVLA_ERR_INVALID; }
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.num_k_blocks = plan->k_blocks; p.k_splits = plan->k_splits; p.kb_per_split = plan->kb_per_split;
+  p.tail_first = plan->tail_first; p.tail_splits = plan->tail_splits; p.tail_kbps = plan->tail_kbps;
+  const Unit u = map_unit(unit, plan->m_tiles * plan->n_tiles, p);
+  if (tile) *tile = u.tile;
+  if (kb0) *kb0 = u.kb0;
+  if (kb1) *kb1 = u.kb1;
+  if (slot) *slot = u.slot;
+  if (split) *split = u.split;
+  return DVLA_OK;
 }
 
 }  // namespace dvla

@@ -74,6 +74,22 @@ typedef struct {
 } dvla_gemm_args;
 int dvla_gemm(const dvla_gemm_args* args, void* stream);
 
+/* What dvla_gemm would launch for `args` (pointers are only tested for NULL and alignment, never dereferenced): host code only,
+ * no CUDA call, so the tiling / split-K / K-split-tail decisions are testable without a GPU (tests/test_gemm_plan_cpu.py).
+ * Work unit u of the persistent kernels covers k-blocks [kb0, kb1) of 64 of output tile `tile` (m fastest); tail_slot >= 0
+ * marks a K-split tail unit (partial sums through the workspace), split its index among the tile's splits. */
+typedef struct dvla_gemm_plan_info {
+  int32_t kernel;                 /* 0 SIMT thread-per-8-outputs, 1 SIMT warp-per-8-outputs, 2 tcgen05 one CTA, 3 tcgen05 CTA pair */
+  int32_t tile_m, tile_n;         /* output tile of one CTA (pair): 128 x {128, 256} or 256 x 256 */
+  int32_t m_tiles, n_tiles, k_blocks;
+  int32_t k_splits, kb_per_split, atomic_out;     /* uniform split-K (weight gradients), bf16 red.global.add when atomic_out */
+  int32_t tail_first, tail_splits, tail_kbps;     /* K-split tail: tiles >= tail_first are cut into tail_splits k-ranges */
+  int32_t units, grid_ctas;
+} dvla_gemm_plan_info;
+int dvla_gemm_plan(const dvla_gemm_args* args, dvla_gemm_plan_info* out);
+int dvla_gemm_plan_unit(const dvla_gemm_plan_info* plan, int32_t unit, int32_t* tile, int32_t* kb0, int32_t* kb1,
+                        int32_t* tail_slot, int32_t* split);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * LayerNorm over the last dim (rows x D), optional affine.  fwd saves mean / rstd (fp32) for the backward.
  * Replaces nn.LayerNorm call sites: gpt2.py:326,333,477; timm Block norm1/norm2; perceiver_resampler.py:14,28-29,101;

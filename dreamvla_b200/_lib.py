@@ -89,7 +89,7 @@ class DitSamplerArgs(C.Structure):
 EXPORTS = [
     "dvla_version", "dvla_last_error", "dvla_launch_count", "dvla_gemm", "dvla_gemm_plan", "dvla_gemm_plan_unit", "dvla_layernorm_fwd", "dvla_layernorm_bwd",
     "dvla_attn_fwd", "dvla_attn_bwd", "dvla_attn_mask_tiles", "dvla_colsum_accum", "dvla_accum_fp32_into_bf16",
-    "dvla_dropout", "dvla_act_bwd", "dvla_act_bwd_colsum", "dvla_cat_broadcast", "dvla_mse_loss", "dvla_cosine_loss", "dvla_silog_stats", "dvla_silog_finish",
+    "dvla_dropout", "dvla_act_bwd", "dvla_act_bwd_colsum", "dvla_cat_broadcast", "dvla_shift_crop", "dvla_resize_nearest", "dvla_mse_loss", "dvla_cosine_loss", "dvla_silog_stats", "dvla_silog_finish",
     "dvla_sumsq", "dvla_adamw", "dvla_grad_clip_scale", "dvla_attn_bwd_workspace_bytes", "dvla_silog_workspace_bytes",
     "dvla_gemm_workspace_bytes", "dvla_set_sm_budget", "dvla_dit_ddim_sample", "dvla_dit_sampler_workspace_bytes",
 ]
@@ -318,6 +318,35 @@ def dropout(x2d, p, seed, out=None, seed_ptr=None):
                                _i64(x2d.stride(0)), _i64(y.stride(0)), _f32(p), _u64(seed), C.c_void_p(_ptr(seed_ptr)),
                                _stream()), "dvla_dropout")
     return y
+
+
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+def shift_crop(x, shifts_xy, pad, out_dtype=None):
+    """out[i, c, y, x] = x[i, c, clamp(y + sy_i - pad), clamp(x + sx_i - pad)]: RandomShiftsAug for given shifts (include/dvla.h).
+    x [n, c, H, W] fp32 / bf16 contiguous, shifts_xy int32 [n, 2] on the same device."""
+    _need_cuda(x, shifts_xy)
+    assert x.dim() == 4 and x.is_contiguous() and x.dtype in _DT
+    n, c, h, w = x.shape
+    assert shifts_xy.dtype == torch.int32 and shifts_xy.shape == (n, 2) and shifts_xy.is_contiguous()
+    out = torch.empty_like(x, dtype=out_dtype or x.dtype)
+    _check(load().dvla_shift_crop(C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), C.c_void_p(shifts_xy.data_ptr()), _i64(n),
+                                  _i64(c), _i64(h), _i64(w), C.c_int32(int(pad)), C.c_int32(_DT[x.dtype]),
+                                  C.c_int32(_DT[out.dtype]), _stream()), "dvla_shift_crop")
+    return out
+
+
+def resize_nearest(x, hout, wout, out_dtype=torch.float32):
+    """torchvision Resize((hout, wout), NEAREST) of a float32 [..., Hin, Win] tensor (depth_image_fn, include/dvla.h)."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() >= 2
+    hin, win = x.shape[-2:]
+    n = x.numel() // (hin * win)
+    out = torch.empty((*x.shape[:-2], hout, wout), device=x.device, dtype=out_dtype)
+    _check(load().dvla_resize_nearest(C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), _i64(n), _i64(hin), _i64(win),
+                                      _i64(hout), _i64(wout), C.c_int32(_DT[out_dtype]), _stream()), "dvla_resize_nearest")
+    return out
 
 
 def act_bwd(dy, pre, act, colsum_out=None):

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdvla_sm100.so")
-SOURCES = ["gemm_sm100.cu", "attention.cu", "attention_small.cu", "attention_fwd_ws.cu", "attention_bwd_ws.cu", "norm_act.cu", "loss_optim.cu", "dit_sampler.cu", "capi.cu"]
+SOURCES = ["gemm_sm100.cu", "attention.cu", "attention_small.cu", "attention_fwd_ws.cu", "attention_bwd_ws.cu", "norm_act.cu", "loss_optim.cu", "dit_sampler.cu", "augment.cu", "capi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",

@@ -36,6 +36,10 @@ int num_sms() {
 
 int gemm_dispatch(const dvla_gemm_args* a, cudaStream_t stream);
 int64_t gemm_workspace_bytes();
+int shift_crop_dispatch(const void* x, void* out, const int32_t* shifts, int64_t n, int64_t c, int64_t h, int64_t w, int32_t pad,
+                        int32_t in_dtype, int32_t out_dtype, cudaStream_t s);
+int resize_nearest_dispatch(const float* x, void* out, int64_t n, int64_t hin, int64_t win, int64_t hout, int64_t wout,
+                            int32_t out_dtype, cudaStream_t s);
 int gemm_plan(const dvla_gemm_args* a, dvla_gemm_plan_info* out);
 int gemm_plan_unit(const dvla_gemm_plan_info* plan, int unit, int* tile, int* kb0, int* kb1, int* slot, int* split);
 int layernorm_fwd_dispatch(const dvla_layernorm_fwd_args* a, cudaStream_t stream);
@@ -104,6 +108,14 @@ int dvla_cat_broadcast(const void* e, const void* m, void* out, int64_t n, int64
 }
 int dvla_act_bwd(const void* dy, const void* pre, void* dx, int64_t n, int32_t act, void* stream) {
   return act_bwd_dispatch(dy, pre, dx, n, act, S(stream));
+}
+int dvla_shift_crop(const void* x, void* out, const int32_t* shifts_xy, int64_t n, int64_t c, int64_t h, int64_t w, int32_t pad,
+                    int32_t in_dtype, int32_t out_dtype, void* stream) {
+  return shift_crop_dispatch(x, out, shifts_xy, n, c, h, w, pad, in_dtype, out_dtype, S(stream));
+}
+int dvla_resize_nearest(const float* x, void* out, int64_t n, int64_t hin, int64_t win, int64_t hout, int64_t wout,
+                        int32_t out_dtype, void* stream) {
+  return resize_nearest_dispatch(x, out, n, hin, win, hout, wout, out_dtype, S(stream));
 }
 int dvla_act_bwd_colsum(const void* dy, const void* pre, void* dx, int64_t rows, int64_t N, int32_t act, float* colsum,
                         void* stream) {

@@ -53,10 +53,14 @@ _FLAGS = [
     ("--pad_length", int, -1), ("--window_size", int, 13), ("--vit_checkpoint_path", str, None),
 ]
 # added by this repo (not in the reference)
+# --device_augment: apply the collator's RandomShiftsAug (--rgb_pad / --gripper_pad / --traj_cons, reference
+# utils/data_utils.py:1337-1354) on the GPU to the transferred batch (utils/data_utils.py here); the loader must then be built
+# WITHOUT pads so that the augmentation is not applied twice.
 # --exchange_on_boundary_only: with gradient accumulation, all-reduce + clip once per optimiser step instead of the
 # reference's every-micro-step exchange and in-place clip (utils/train_utils.py:599-600); a different update, opt-in.
 _EXTRA = [("--synthetic_steps", int, 0), ("--cuda_graph", "flag", False), ("--synthetic_rollout_steps", int, 0),
-          ("--exchange_on_boundary_only", "flag", False), ("--incremental_rollout", "flag", False)]
+          ("--exchange_on_boundary_only", "flag", False), ("--incremental_rollout", "flag", False),
+          ("--device_augment", "flag", False)]
 
 
 def get_parser() -> argparse.ArgumentParser:

@@ -755,8 +755,13 @@ def train_one_epoch_calvin(args, model, epoch, calvin_loader, optimizer, lr_sche
     accum = args.gradient_accumulation_steps
     state.micro = 0           # the reference counts accumulation windows from the start of each epoch (:602)
     graphed = getattr(core, "_dvla_graphed_step", None)
+    device_augment = bool(getattr(args, "device_augment", False)) and (getattr(args, "rgb_pad", -1) != -1
+                                                                        or getattr(args, "gripper_pad", -1) != -1)
     for num_steps, batch in enumerate(prefetch_to_device(calvin_loader, dev, batch_to_host_dict)):
         data_time_m.update(time.time() - end)
+        if device_augment:        # the collator's random shifts (reference data_utils.py:1337-1354), on the device
+            from .data_utils import augment_batch
+            batch = augment_batch(batch, args.rgb_pad, args.gripper_pad, bool(getattr(args, "traj_cons", False)))
         lr = lr_scheduler.get_last_lr()[0] if lr_scheduler is not None else args.learning_rate
         if use_graph and graphed is None and state.total_micro > 0:
             graphed = GraphedTrainStep(state, batch, warmup=0)

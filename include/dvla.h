@@ -272,6 +272,21 @@ typedef struct {
 int64_t dvla_dit_sampler_workspace_bytes(int64_t batch, int64_t T, int64_t hidden, int64_t mlp, int64_t n_steps);
 int dvla_dit_ddim_sample(const dvla_dit_sampler_args* args, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Device-side pieces of the reference's collator (utils/data_utils.py:1337-1354).  dtype codes: 0 fp32, 1 bf16.
+ *
+ * dvla_shift_crop = RandomShiftsAug.forward / forward_traj (utils/data_utils.py:326-383) for GIVEN integer shifts:
+ *   out[i, c, y, x] = x[i, c, clamp(y + sy_i - pad, 0, H-1), clamp(x + sx_i - pad, 0, W-1)],  shifts_xy int32 [n, 2] = (sx, sy)
+ *   in [0, 2*pad] (the reference draws them with torch.randint(0 | 1, 2*pad+1) per image / per frame and feeds them to
+ *   grid_sample on the replicate-padded image; every sample point is a pixel centre, so the op is this clamped crop).
+ *   x, out: [n, c, H, W] contiguous; n = batch * frames for forward_traj.
+ * dvla_resize_nearest = torchvision Resize((hout, wout), NEAREST) of depth_image_fn (utils/data_utils.py:3588-3603):
+ *   out[i, y, x] = x[i, min(floor(y * hin/hout), hin-1), min(floor(x * win/wout), win-1)], scales in fp32 as torch computes them. */
+int dvla_shift_crop(const void* x, void* out, const int32_t* shifts_xy, int64_t n, int64_t c, int64_t h, int64_t w, int32_t pad,
+                    int32_t in_dtype, int32_t out_dtype, void* stream);
+int dvla_resize_nearest(const float* x_f32, void* out, int64_t n, int64_t hin, int64_t win, int64_t hout, int64_t wout,
+                        int32_t out_dtype, void* stream);
+
 /* SM budget of the persistent GEMM kernels (one CTA / CTA pair per SM).  0 = all SMs (default).  The data-parallel train
  * step lowers it by the number of CTAs the NCCL all-reduce occupies while gradient exchange overlaps the backward pass
  * (train.py:173 DDP overlap), so that every GEMM CTA is resident at once.  Returns the previous value.  Process-wide. */

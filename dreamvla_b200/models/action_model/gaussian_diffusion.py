@@ -151,6 +151,27 @@ class SpacedDiffusion(GaussianDiffusion):
         return img
 
 
+class FMDiffusion(GaussianDiffusion):
+    """Flow-matching sampler of `--use_fm` (reference respace.py:118-191): NOT a diffusion process -- the betas only fix
+    `num_timesteps` -- but an explicit Euler integration of the predicted velocity over t = 0, 1/T, ..., (T-1)/T."""
+
+    @torch.no_grad()
+    def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=False, model_kwargs=None, device=None,
+                         progress=False, eta=0.0, start=None):
+        """respace.py:122-156.  As in the reference the guidance scale is forced to 1.0 and the `noise` argument is IGNORED:
+        the start state is drawn here, [shape] fp32 (`start=` injects it for parity tests); `final += (1/T) * u_t`."""
+        model_kwargs = dict(model_kwargs or {})
+        if "cfg_scale" in model_kwargs:
+            model_kwargs["cfg_scale"] = 1.0                                              # :136-138
+        final = start.to(device=device, dtype=torch.float32) if start is not None else torch.randn(*shape, device=device)
+        delta = 1.0 / self.num_timesteps
+        for i in range(self.num_timesteps):
+            t = torch.full((shape[0],), float(i), device=final.device) / self.num_timesteps       # :144-145
+            ut = model(final, t, **model_kwargs)                                         # p_sample -> p_mean_variance :158-172
+            final = final + delta * ut
+        return final
+
+
 def create_diffusion(timestep_respacing, noise_schedule="linear", diffusion_steps=1000, **_unused):
     """action_model/__init__.py:10-46 (epsilon / fixed-small / MSE configuration)."""
     betas = get_named_beta_schedule(noise_schedule, diffusion_steps)

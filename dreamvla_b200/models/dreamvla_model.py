@@ -12,7 +12,7 @@ What differs, by design (B200-first, results identical up to bf16 rounding):
   * the ViT patch-token permutation of random_masking(…, 0.0) is skipped (outputs invariant, see vit_mae.py here);
   * identical sentences are CLIP-encoded once.
 Out of scope (need code/weights that are not in the reference tree): use_dinosiglip, use_gpt2_pretrained,
-use_dpt_head, use_fm.  They raise NotImplementedError.
+use_dpt_head.  They raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -26,7 +26,7 @@ from torch import nn
 
 from .. import ops
 from . import clip_text
-from .action_model import ActionModel
+from .action_model import ActionModel, ActionModelFM
 from .gpt2 import GPT2Config, GPT2Model
 from .layers import Block, LayerNorm, Linear
 from .perceiver_resampler import PerceiverResampler
@@ -209,7 +209,7 @@ class DreamVLA(nn.Module):
     ):
         super().__init__()
         for flag, name in ((use_dinosiglip, "use_dinosiglip"), (use_gpt2_pretrained, "use_gpt2_pretrained"),
-                           (use_dpt_head, "use_dpt_head"), (use_fm, "use_fm")):
+                           (use_dpt_head, "use_dpt_head")):
             if flag:
                 raise NotImplementedError(f"{name}: needs weights/code outside the reference tree (out of scope, SURVEY §8a)")
         self.finetune_type = finetune_type
@@ -370,9 +370,11 @@ class DreamVLA(nn.Module):
             self.traj_decoder_position_embedding = nn.Parameter(torch.zeros(1, num_obs_token_per_image + self.NUM_TRAJ_MASK_TOKEN, D), requires_grad=False)
 
         self.use_dit_head = use_dit_head
+        self.use_fm = bool(use_fm) and bool(use_dit_head)
         if self.use_dit_head:
-            self.action_model = ActionModel(model_type=dit_type, token_size=D, in_channels=7,
-                                            future_action_window_size=self.action_pred_steps - 1, past_action_window_size=0)
+            action_model_cls = ActionModelFM if use_fm else ActionModel                   # :450
+            self.action_model = action_model_cls(model_type=dit_type, token_size=D, in_channels=7,
+                                                 future_action_window_size=self.action_pred_steps - 1, past_action_window_size=0)
         else:
             self.action_decoder = nn.Sequential(Linear(D, MLP_hidden_dim), nn.ReLU(), Linear(MLP_hidden_dim, MLP_hidden_dim), nn.ReLU())
             self.arm_action_decoder = nn.Sequential(Linear(MLP_hidden_dim, 6), nn.Tanh())
@@ -506,6 +508,22 @@ class DreamVLA(nn.Module):
         """10-step DDIM with classifier-free guidance 1.5 (:935-987) on feat [n, action_pred_steps, D] -> [n, steps, 7]."""
         bs = feat.shape[0]
         cfg_scale = 1.5
+        if self.use_fm:
+            # --use_fm (ActionModelFM / FMDiffusion, respace.py:118-191): the sampler forces the guidance scale to 1.0, ignores
+            # the noise it is handed and draws its own start state [2 bs, steps, 7]; `sample_noise` (parity tests) injects
+            # that state ([2 bs, ...], or [bs, ...] used for both halves -- only the first half reaches the output)
+            uncondition = self.action_model.net.z_embedder.uncondition.unsqueeze(0).expand(bs, self.action_pred_steps, -1)
+            z = torch.cat([feat, uncondition], 0)
+            if self.action_model.ddim_diffusion is None:
+                self.action_model.create_ddim(ddim_step=10)
+            start = None
+            if sample_noise is not None:
+                start = sample_noise if sample_noise.shape[0] == 2 * bs else torch.cat([sample_noise, sample_noise], 0)
+            shape = (2 * bs, self.action_pred_steps, self.action_model.in_channels)
+            samples = self.action_model.ddim_diffusion.ddim_sample_loop(
+                self.action_model.net.forward_with_cfg, shape, None, clip_denoised=False,
+                model_kwargs=dict(z=z, cfg_scale=cfg_scale), device=dev, eta=0.0, start=start)
+            return samples.chunk(2, dim=0)[0].to(feat.dtype)
         if sample_noise is None:
             sample_noise = torch.randn(bs, self.action_pred_steps, self.action_model.in_channels, device=dev)
         noise = sample_noise.to(device=dev, dtype=feat.dtype)

@@ -331,11 +331,38 @@ def dreamvla_forward(sd, cfg, image_primary, image_wrist, state, text_token, act
             lab = action_label.flatten(0, 1)
             x0 = lab.repeat(8, 1, 1)
             z = feat.repeat(8, 1, 1)
-            diff = Diffusion()
-            xt = diff.q_sample(x0, diffusion_timestep, diffusion_noise)
-            pred = dit_forward(sd, xt, diffusion_timestep, z, diffusion_drop_ids)
-            out["noise_pred"] = pred
-            out["loss_action"] = ((pred - diffusion_noise) ** 2).mean()
+            if cfg.get("use_fm", False):
+                # ActionModelFM.loss (action_model.py:118-139): T = 10 "diffusion steps", t = randint(0, T) / T,
+                # x_t = t x + (1 - t) noise, the net predicts the velocity u = x - noise
+                tt = diffusion_timestep.float() / 10
+                xt = tt.view(-1, 1, 1) * x0 + (1 - tt.view(-1, 1, 1)) * diffusion_noise
+                pred = dit_forward(sd, xt, tt, z, diffusion_drop_ids)
+                out["noise_pred"] = pred
+                out["loss_action"] = ((pred - (x0 - diffusion_noise)) ** 2).mean()
+            else:
+                diff = Diffusion()
+                xt = diff.q_sample(x0, diffusion_timestep, diffusion_noise)
+                pred = dit_forward(sd, xt, diffusion_timestep, z, diffusion_drop_ids)
+                out["noise_pred"] = pred
+                out["loss_action"] = ((pred - diffusion_noise) ** 2).mean()
+        elif cfg.get("use_fm", False):
+            # FMDiffusion.ddim_sample_loop (respace.py:122-156): guidance scale forced to 1.0, the start state is drawn inside
+            # the loop ([2 bs, T, 7]; `sample_noise` here) and the `noise` argument is ignored, 10 Euler steps of 1/10
+            feat = feat.flatten(0, 1)
+            bs = feat.shape[0]
+            unc = sd["action_model.net.z_embedder.uncondition"].unsqueeze(0).expand(bs, act_steps, -1)
+            z = torch.cat([feat, unc], 0)
+            final = sample_noise.clone()
+            for i in range(10):
+                t = torch.full((final.shape[0],), float(i)) / 10
+                half = final[: len(final) // 2]
+                mo = dit_forward(sd, torch.cat([half, half], 0), t.to(final.device), z)
+                ce, ue = torch.split(mo, len(mo) // 2, dim=0)
+                he = ue + 1.0 * (ce - ue)                                    # models.py:262-266 with cfg_scale = 1.0
+                final = final + (1 / 10) * torch.cat([he, he], 0).to(final.dtype)
+            samples = final.chunk(2, dim=0)[0]
+            out["arm_pred_action"] = samples.unsqueeze(0)[..., :6]
+            out["gripper_pred_action"] = samples.unsqueeze(0)[..., 6:]
         else:
             feat = feat.flatten(0, 1)
             bs = feat.shape[0]

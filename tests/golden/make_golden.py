@@ -55,6 +55,8 @@ class Capture:
         self._orig = {n: getattr(torch, n) for n in ("randn_like", "randint", "rand", "randn")}
         for n, f in self._orig.items():
             def wrap(*a, _f=f, _n=n, **k):
+                if k.get("device") == "cuda":          # FMDiffusion.ddim_sample_loop hard-codes device='cuda' (respace.py:139)
+                    k.pop("device")
                 t = _f(*a, **k)
                 self.draws.append((_n, t.clone()))
                 return t
@@ -123,6 +125,9 @@ def run_case(name, cfg):
             out_t = model(inputs["image_primary"], inputs["image_wrist"], inputs["state"], inputs["text_token"], mode="test")
         assert cap.draws[0][0] == "randn", [d[0] for d in cap.draws][:3]
         tensors["sample_noise"] = cap.draws[0][1]
+        if cfg.get("use_fm", False):               # the loop ignores that noise and draws its own start state [2 bs, T, 7]
+            assert [d[0] for d in cap.draws] == ["randn", "randn"] and cap.draws[1][1].shape[0] == 2 * cap.draws[0][1].shape[0]
+            tensors["sample_noise"] = cap.draws[1][1]
         tensors["test_arm"], tensors["test_gripper"] = out_t[0].clone(), out_t[1].clone()
     # ---- mask (bit-exact contract) ----
     vis = (model.attention_mask == 0)
@@ -140,6 +145,6 @@ def run_case(name, cfg):
 if __name__ == "__main__":
     torch.set_num_threads(8)
     only = sys.argv[1:]
-    for name, cfg in {**synth.CASES, **synth.CPU_ONLY_CASES, **synth.FULL_CASES}.items():
+    for name, cfg in {**synth.CASES, **synth.CPU_ONLY_CASES, **synth.FULL_CASES, **synth.FM_CASES}.items():
         if not only or name in only:
             run_case(name, cfg)

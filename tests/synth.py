@@ -34,6 +34,14 @@ CPU_ONLY_CASES = {
                                  sam_feat_pred=False, use_dit_head=True, sequence_length=3, gripper_width=True),
 }
 
+# Flow-matching action head (`--use_fm`, eval_libero.py:75; ActionModelFM / FMDiffusion): reference -> golden -> oracle on the
+# CPU, CUDA path in tests/test_model_gpu.py::test_flow_matching_head
+FM_CASES = {
+    "libero_fm": dict(BASE, obs_pred=False, depth_pred=False, trajectory_pred=False, dino_feat_pred=False,
+                      sam_feat_pred=False, use_dit_head=True, sequence_length=3, use_fm=True, weight_seed=41, input_seed=42,
+                      draw_seed=43),
+}
+
 # Full-depth cases: BASELINE.json's C2 (CALVIN, 24 layers, S=10, five world heads + DiT, L=1290) and C3 (LIBERO, S=7,
 # --gripper_width, world heads off, L=273) at batch 1.  GPU parity only (tests/test_full_depth_gpu.py); the reference runs
 # them on the CPU in fp32 in ~1 min each when the goldens are generated.
@@ -50,7 +58,7 @@ CTOR_KEYS = ("sequence_length", "num_resampler_query", "num_obs_token_per_image"
              "attn_robot_proprio_state", "atten_goal", "atten_goal_state", "mask_l_obs_ratio", "action_pred_steps",
              "transformer_layers", "hidden_dim", "transformer_heads", "phase", "gripper_width", "pred_num", "depth_pred",
              "trajectory_pred", "track_label_patch_size", "dino_feat_pred", "sam_feat_pred", "use_dit_head",
-             "attn_implementation")
+             "attn_implementation", "use_fm")
 
 
 def ctor_kwargs(cfg):

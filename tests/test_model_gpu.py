@@ -45,10 +45,10 @@ def dev():
     return torch.device("cuda:0")
 
 
-@pytest.mark.parametrize("name", list(synth.CASES) + list(synth.CPU_ONLY_CASES))
+@pytest.mark.parametrize("name", list(synth.CASES) + list(synth.CPU_ONLY_CASES) + list(synth.FM_CASES))
 def test_forward_matches_oracle_and_golden(name, dev):
     from oracle import dreamvla_oracle as O
-    cfg = {**synth.CASES, **synth.CPU_ONLY_CASES}[name]
+    cfg = {**synth.CASES, **synth.CPU_ONLY_CASES, **synth.FM_CASES}[name]
     fx = json.load(open(os.path.join(GOLDEN, f"{name}.json")))
     gold = torch.load(os.path.join(GOLDEN, f"{name}.pt"))
     model, sd = build(cfg, dev)
@@ -81,6 +81,42 @@ def test_forward_matches_oracle_and_golden(name, dev):
     else:
         assert rel(synth.subsample(out[0]), gold["arm_sub"]) < 2e-2
         assert rel(synth.subsample(out[1]), gold["gripper_sub"]) < 2e-2
+
+
+def test_flow_matching_head_backward(dev):
+    """`--use_fm` (ActionModelFM): gradients of the flow-matching loss vs autograd through the fp32 oracle, same draws."""
+    from oracle import dreamvla_oracle as O
+    name = "libero_fm"
+    cfg = synth.FM_CASES[name]
+    gold = torch.load(os.path.join(GOLDEN, f"{name}.pt"))
+    model, sd = build(cfg, dev)
+    from dreamvla_b200.models.action_model import ActionModelFM, FMDiffusion
+    assert isinstance(model.action_model, ActionModelFM) and model.action_model.diffusion.num_timesteps == 10
+    assert isinstance(model.action_model.create_ddim(10), FMDiffusion)
+    model.train()
+    inp = synth.synth_inputs(cfg)
+    dinp = {k: v.to(dev) for k, v in inp.items()}
+    out = model(dinp["image_primary"], dinp["image_wrist"], dinp["state"], dinp["text_token"], action_label=dinp["action_label"],
+                diffusion_noise=gold["diffusion_noise"].to(dev), diffusion_timestep=gold["diffusion_timestep"].to(dev),
+                diffusion_drop_ids=gold["diffusion_drop_ids"].to(dev).long())
+    out[0].float().backward()
+    frozen = ("vision_encoder.", "clip_model.", "attention_mask", "position_embedding")
+    osd = {k: v.clone() for k, v in sd.items()}
+    for k, v in osd.items():
+        if v.is_floating_point() and not any(f in k for f in frozen) or k == "transformer_backbone_position_embedding":
+            v.requires_grad_(True)
+    fwd = O.dreamvla_forward(osd, cfg, inp["image_primary"], inp["image_wrist"], inp["state"], inp["text_token"],
+                             action_label=inp["action_label"], diffusion_noise=gold["diffusion_noise"],
+                             diffusion_timestep=gold["diffusion_timestep"], diffusion_drop_ids=gold["diffusion_drop_ids"])
+    fwd["loss_action"].backward()
+    assert abs(float(out[0]) - float(fwd["loss_action"])) < 2e-2 * abs(float(fwd["loss_action"]))
+    params = dict(model.named_parameters())
+    worst = [(rel(params[k].grad, osd[k].grad), k) for k in (
+        "action_model.net.blocks.0.attn.qkv.weight", "action_model.net.blocks.11.mlp.fc2.weight",
+        "action_model.net.final_layer.linear.weight", "action_model.net.t_embedder.mlp.0.weight",
+        "action_model.net.x_embedder.linear.weight", "action_pred_token", "transformer_backbone.h.1.mlp.c_proj.weight")]
+    bad = [(e, k) for e, k in worst if not e < 6e-2]
+    assert not bad, f"gradient mismatch: {bad}"
 
 
 def test_backward_matches_oracle(dev):

@@ -24,9 +24,9 @@ def template_state(cfg):
     return build_template(cfg)
 
 
-@pytest.mark.parametrize("name", list(synth.CASES) + list(synth.CPU_ONLY_CASES))
+@pytest.mark.parametrize("name", list(synth.CASES) + list(synth.CPU_ONLY_CASES) + list(synth.FM_CASES))
 def test_oracle_matches_reference_golden(name):
-    cfg = {**synth.CASES, **synth.CPU_ONLY_CASES}[name]
+    cfg = {**synth.CASES, **synth.CPU_ONLY_CASES, **synth.FM_CASES}[name]
     fx = json.load(open(os.path.join(GOLDEN, f"{name}.json")))
     gold = torch.load(os.path.join(GOLDEN, f"{name}.pt"))
     torch.set_num_threads(min(8, os.cpu_count() or 1))

@@ -33,22 +33,23 @@ template <typename T> __device__ __forceinline__ void st_from_float(T* p, float 
 template <> __device__ __forceinline__ void st_from_float<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void st_from_float<bf16>(bf16* p, float v) { *p = __float2bfloat16(v); }
 
-// thread = one output element, x fastest: reads of a row stay contiguous (shifted by sx) except at the clamped borders
+// warp = one output row (img, channel, y) at a time, lanes stride x: the index arithmetic (two divisions, the clamp of y) is done
+// once per row, reads of a row are contiguous (shifted by sx) except at the clamped borders, writes are contiguous
 template <typename Tin, typename Tout>
 __global__ void __launch_bounds__(256) shift_crop_kernel(const Tin* __restrict__ x, Tout* __restrict__ out,
                                                          const int* __restrict__ shifts, long long n, int c, int h, int w, int pad) {
-  const long long plane = static_cast<long long>(h) * w;
-  const long long total = n * c * plane;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long img = i / (c * plane);
-    const long long rem = i - img * c * plane;
-    const int ch = static_cast<int>(rem / plane);
-    const int yx = static_cast<int>(rem - static_cast<long long>(ch) * plane);
-    const int y = yx / w, xx = yx - y * w;
+  const int lane = threadIdx.x & 31;
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const long long rows = n * c * h;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const long long img = r / (static_cast<long long>(c) * h);
+    const int y = static_cast<int>(r % h);
     const int sx = __ldg(shifts + 2 * img), sy = __ldg(shifts + 2 * img + 1);
-    const int ys = min(max(y + sy - pad, 0), h - 1), xs = min(max(xx + sx - pad, 0), w - 1);
-    st_from_float(out + i, ld_as_float(x + (img * c + ch) * plane + static_cast<long long>(ys) * w + xs));
+    const int ys = min(max(y + sy - pad, 0), h - 1);
+    const Tin* src = x + (r - y + ys) * w;            // same image and channel, source row ys
+    Tout* dst = out + r * w;
+    for (int xx = lane; xx < w; xx += 32) st_from_float(dst + xx, ld_as_float(src + min(max(xx + sx - pad, 0), w - 1)));
   }
 }
 
@@ -76,11 +77,11 @@ static unsigned grid_for(long long total) {
 // dtype codes: 0 = fp32, 1 = bf16
 int shift_crop_dispatch(const void* x, void* out, const int32_t* shifts, int64_t n, int64_t c, int64_t h, int64_t w, int32_t pad,
                         int32_t in_dtype, int32_t out_dtype, cudaStream_t s) {
+  if (n == 0) return DVLA_OK;
   if (!x || !out || !shifts) { set_error("shift_crop: null pointer"); return DVLA_ERR_INVALID; }
   if (n < 0 || c <= 0 || h <= 0 || w <= 0 || pad < 0 || h > 32768 || w > 32768 || c > 65535) { set_error("shift_crop: bad dims"); return DVLA_ERR_INVALID; }
   if ((in_dtype | out_dtype) & ~1) { set_error("shift_crop: dtype codes are 0 (fp32) / 1 (bf16)"); return DVLA_ERR_INVALID; }
-  if (n == 0) return DVLA_OK;
-  const unsigned g = grid_for(n * c * h * w);
+  const unsigned g = grid_for(n * c * h * 32);          // one warp per row
 #define SC(TI, TO) shift_crop_kernel<TI, TO><<<g, 256, 0, s>>>((const TI*)x, (TO*)out, shifts, n, (int)c, (int)h, (int)w, pad)
   switch (in_dtype * 2 + out_dtype) {
     case 0: SC(float, float); break;
@@ -95,6 +96,7 @@ int shift_crop_dispatch(const void* x, void* out, const int32_t* shifts, int64_t
 
 int resize_nearest_dispatch(const float* x, void* out, int64_t n, int64_t hin, int64_t win, int64_t hout, int64_t wout,
                             int32_t out_dtype, cudaStream_t s) {
+  if (n == 0) return DVLA_OK;
   if (!x || !out) { set_error("resize_nearest: null pointer"); return DVLA_ERR_INVALID; }
   if (n < 0 || hin <= 0 || win <= 0 || hout <= 0 || wout <= 0 || hin > 32768 || win > 32768 || hout > 32768 || wout > 32768) {
     set_error("resize_nearest: bad dims"); return DVLA_ERR_INVALID;

@@ -84,7 +84,34 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.stop_flag = threading.Event()
 
+    def _nvml_loop(self):
+        """NVML (nvidia_ml_py) polled every 20 ms: one nvidia-smi process takes ~0.5 s to answer, which leaves a 1.6 s timed
+        region with one or two samples.  Same fields as the nvidia-smi query; any failure falls back to nvidia-smi."""
+        import pynvml as N
+        N.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = self.gpu_index
+        if vis:                                  # NVML enumerates physical devices, CUDA the visible subset
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.gpu_index < len(ids) and ids[self.gpu_index].isdigit():
+                idx = int(ids[self.gpu_index])
+        h = N.nvmlDeviceGetHandleByIndex(idx)
+        mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+        bits = (("hw_slowdown", N.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", N.nvmlClocksEventReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", N.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", N.nvmlClocksEventReasonSwPowerCap))
+        while not self.stop_flag.is_set():
+            sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+            r = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+            pw = N.nvmlDeviceGetPowerUsage(h) / 1000.0
+            self.samples.append([str(idx), str(sm), str(mx), f"{pw:.1f}"] + ["Active" if r & b else "Not Active" for _, b in bits])
+            self.stop_flag.wait(0.02)
+
     def run(self):
+        try:
+            self._nvml_loop()
+            return
+        except Exception:  # noqa: BLE001   (no NVML binding / driver mismatch: the nvidia-smi recipe)
+            pass
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
